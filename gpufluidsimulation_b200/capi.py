@@ -1,0 +1,149 @@
+"""ctypes binding of include/bimocq_b200.h.  Argument order and meaning are the header's."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+_LIB = None
+
+
+class BimocqLibraryError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_PKG, "lib", "libbimocq_b200.so")
+
+
+def header_path() -> str:
+    return os.path.join(_ROOT, "include", "bimocq_b200.h")
+
+
+def build_library(clean: bool = False) -> str:
+    """nvcc-compile csrc/*.cu for sm_100a into lib/libbimocq_b200.so (in-tree)."""
+    csrc = os.path.join(_PKG, "csrc")
+    if clean:
+        subprocess.check_call(["make", "-C", csrc, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", csrc, "-j4"], stdout=subprocess.DEVNULL)
+    return library_path()
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/bimocq_b200.h declares."""
+    text = open(header_path()).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:gpu|bmq3d|bmq2d|bmq)_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+_F = C.POINTER(C.c_float)
+_I = C.c_int
+_f = C.c_float
+_H = C.c_void_p  # bmq3d_solver*
+
+
+class Stats3D(C.Structure):
+    _fields_ = [("max_v", _f), ("cfldt", _f), ("n_substeps", _I), ("vel_distortion", _f),
+                ("scalar_distortion", _f), ("vel_reinit", _I), ("scalar_reinit", _I),
+                ("vel_reinit_count", _I), ("scalar_reinit_count", _I), ("max_disp_z", _f)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# field ids (keep in step with the enum in include/bimocq_b200.h; tests/test_capi_symbols.py checks)
+FIELD_NAMES = [
+    "U", "V", "W", "RHO", "T", "U_INIT", "V_INIT", "W_INIT", "RHO_INIT", "T_INIT",
+    "U_PREV", "V_PREV", "W_PREV", "RHO_PREV", "T_PREV",
+    "DU_EXT", "DV_EXT", "DW_EXT", "DRHO_EXT", "DT_EXT", "DU_PROJ", "DV_PROJ", "DW_PROJ",
+    "VFWD_X", "VFWD_Y", "VFWD_Z", "VBWD_X", "VBWD_Y", "VBWD_Z", "VBWDP_X", "VBWDP_Y", "VBWDP_Z",
+    "SFWD_X", "SFWD_Y", "SFWD_Z", "SBWD_X", "SBWD_Y", "SBWD_Z", "SBWDP_X", "SBWDP_Y", "SBWDP_Z",
+    "U_SEMI", "V_SEMI", "W_SEMI", "RHO_SEMI", "T_SEMI",
+]
+FIELD = {n: i for i, n in enumerate(FIELD_NAMES)}
+FIELD.update({n: 64 + i for i, n in enumerate(
+    ["U_ADV", "V_ADV", "W_ADV", "RHO_ADV", "T_ADV", "U_ERR", "V_ERR", "W_ERR", "RHO_ERR", "T_ERR"])})
+
+_PROTOS = {
+    "bmq_last_error": (C.c_char_p, []),
+    "bmq_clear_error": (_I, []),
+    "bmq_version": (C.c_char_p, []),
+    "bmq_kernel_launch_count": (C.c_ulonglong, []),
+    "gpu_solve_forward": (None, [_F] * 6 + [_f, _I, _I, _I, _f, _f]),
+    "gpu_solve_backwardDMC": (None, [_F] * 9 + [_f, _I, _I, _I, _f]),
+    "gpu_advect_velocity": (None, [_F] * 9 + [_f, _I, _I, _I, C.c_bool]),
+    "gpu_advect_vel_double": (None, [_F] * 12 + [_f, _I, _I, _I, C.c_bool, _f]),
+    "gpu_advect_field": (None, [_F] * 5 + [_f, _I, _I, _I, C.c_bool]),
+    "gpu_advect_field_double": (None, [_F] * 8 + [_f, _I, _I, _I, C.c_bool, _f]),
+    "gpu_accumulate_velocity": (None, [_F] * 9 + [_f, _I, _I, _I, C.c_bool, _f]),
+    "gpu_accumulate_field": (None, [_F] * 5 + [_f, _I, _I, _I, C.c_bool, _f]),
+    "gpu_estimate_distortion": (None, [_F] * 7 + [_f, _I, _I, _I]),
+    "gpu_add": (None, [_F, _F, _f, _I]),
+    "gpu_compensate_velocity": (None, [_F] * 15 + [_f, _I, _I, _I, C.c_bool]),
+    "gpu_compensate_field": (None, [_F] * 9 + [_f, _I, _I, _I, C.c_bool]),
+    "gpu_semilag": (None, [_F] * 5 + [_I, _I, _I, _f, _I, _I, _I, _f, _f]),
+    "gpu_add_field": (None, [_F, _F, _F, _f, _I]),
+    "bmq3d_create": (_I, [_I, _I, _I, _f, _f, C.POINTER(_H)]),
+    "bmq3d_create_slab": (_I, [_I, _I, _I, _f, _f, _I, _I, _I, C.POINTER(_H)]),
+    "bmq3d_destroy": (_I, [_H]),
+    "bmq3d_set_stream": (_I, [_H, C.c_void_p]),
+    "bmq3d_field_ptr": (_I, [_H, _I, C.POINTER(C.c_void_p), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "bmq3d_upload": (_I, [_H, _I, C.c_void_p]),
+    "bmq3d_download": (_I, [_H, _I, C.c_void_p]),
+    "bmq3d_reset": (_I, [_H]),
+    "bmq3d_advect": (_I, [_H, _I, _f, _I]),
+    "bmq3d_accumulate": (_I, [_H, _I, _f]),
+    "bmq3d_get_stats": (_I, [_H, C.POINTER(Stats3D)]),
+    "bmq3d_advect_host": (_I, [_H, _I, _f] + [C.c_void_p] * 5),
+    "bmq3d_accumulate_host": (_I, [_H, _I, _f] + [C.c_void_p] * 8),
+    "bmq3d_stage_maxvel": (_I, [_H, C.POINTER(_f)]),
+    "bmq3d_stage_set_cfl": (_I, [_H, _I, _f]),
+    "bmq3d_stage_dmc_substep": (_I, [_H, _f]),
+    "bmq3d_stage_forward": (_I, [_H, _f]),
+    "bmq3d_stage_semilag": (_I, [_H, _f]),
+    "bmq3d_stage_advect": (_I, [_H, _I]),
+    "bmq3d_stage_error": (_I, [_H, _I]),
+    "bmq3d_stage_apply": (_I, [_H, _I]),
+    "bmq3d_stage_blend": (_I, [_H, _I]),
+    "bmq3d_stage_distortion": (_I, [_H, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f)]),
+    "bmq3d_stage_decide": (_I, [_H, _I, _f, _f, _f]),
+    "bmq3d_stage_accumulate": (_I, [_H, _I]),
+    "bmq3d_stage_reinit": (_I, [_H, _I, _I]),
+}
+
+
+def load_library():
+    """dlopen lib/libbimocq_b200.so and attach prototypes.  Raises (never falls back) if missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise BimocqLibraryError(
+            f"{path} has not been built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or make -C gpufluidsimulation_b200/csrc).  There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)   # AttributeError here = header/library mismatch, which must be loud
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load_library().bmq_last_error().decode(errors="replace")
+        raise BimocqLibraryError(f"{what or 'libbimocq_b200'} failed with status {status}: {msg}")
+
+
+def check_legacy(what: str = "") -> None:
+    """The legacy gpu_* symbols return void; surface a latched error as an exception."""
+    lib = load_library()
+    msg = lib.bmq_last_error().decode(errors="replace")
+    code = lib.bmq_clear_error()
+    if code != 0:
+        raise BimocqLibraryError(f"{what or 'gpu_*'} latched error {code}: {msg}")

@@ -1,0 +1,75 @@
+// Error latch, version and launch counter of libbimocq_b200.so.
+#include "common.h"
+#include "launch3d.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+namespace bmq {
+
+static std::mutex g_err_mutex;
+static std::string g_err_msg;
+static int g_err_code = BMQ_OK;
+
+int set_error(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_err_msg = buf;
+    g_err_code = code;
+    return code;
+}
+
+int check_cuda(cudaError_t e, const char *what, const char *file, int line)
+{
+    if (e == cudaSuccess) return BMQ_OK;
+    return set_error(BMQ_ERR_CUDA, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file,
+                     line, what);
+}
+
+bool require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error(BMQ_ERR_NODEVICE,
+                  "libbimocq_b200: no CUDA device visible (%s); there is no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return false;
+    }
+    return true;
+}
+
+}  // namespace bmq
+
+extern "C" {
+
+const char *bmq_last_error(void)
+{
+    // the returned pointer stays valid until the next error is latched
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(bmq::g_err_mutex);
+    copy = bmq::g_err_msg;
+    return copy.c_str();
+}
+
+int bmq_clear_error(void)
+{
+    std::lock_guard<std::mutex> lk(bmq::g_err_mutex);
+    int c = bmq::g_err_code;
+    bmq::g_err_code = BMQ_OK;
+    bmq::g_err_msg.clear();
+    return c;
+}
+
+const char *bmq_version(void) { return "bimocq_b200 0.1 (sm_100a)"; }
+
+unsigned long long bmq_kernel_launch_count(void) { return bmq::kernel_launch_count(); }
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// Device-side building blocks of the 3D BiMocq^2 advection kernels (sm_100a).
+//
+// Numerics contract (DESIGN.md "Numerics"): fp32 storage and fp32 arithmetic with the
+// interpolation nest in the reference's order x -> y -> z (GPU_kernel.cu:27-41).  The reference
+// lerp (GPU_kernel.cu:22-25) evaluates (1.0-c)*a in double and c*b in float; here it is
+// fmaf(1-c, a, c*b): the same float product c*b, one fused rounding of the sum, no FP64 and no
+// F2F conversions.  Positions -> (cell, fraction) use the reference's expression
+// floorf(p/h), p/h - i (GPU_kernel.cu:46-51) with an IEEE division; when h is a power of two
+// the division is replaced by an exact multiplication (template parameter P2), which is
+// bit-identical.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bmq {
+
+struct Grid3 {
+    int ni, nj, nk;   // global cell counts
+    float h, inv_h;   // cell size; 1/h (exact when h is a power of two)
+};
+
+struct Frac {
+    int i;
+    float f, omf;
+};
+
+template <bool P2>
+__device__ __forceinline__ Frac split(float p, float h, float inv_h)
+{
+    float q = P2 ? p * inv_h : __fdiv_rn(p, h);
+    float fl = floorf(q);
+    Frac r;
+    r.i = (int)fl;
+    r.f = q - fl;
+    r.omf = 1.0f - r.f;
+    return r;
+}
+
+__device__ __forceinline__ float lerp32(float a, float b, float f, float omf)
+{
+    return fmaf(omf, a, f * b);
+}
+
+__device__ __forceinline__ float clampf(float a, float lo, float hi)
+{
+    return fminf(fmaxf(lo, a), hi);
+}
+
+// Trilinear sample of a dense x-fastest array; p points at node (x.i, y.i, z.i).
+__device__ __forceinline__ float tri8(const float *__restrict__ p, int sy, int sz, const Frac &x,
+                                      const Frac &y, const Frac &z)
+{
+    float v000 = __ldg(p), v001 = __ldg(p + 1);
+    float v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
+    float v100 = __ldg(p + sz), v101 = __ldg(p + sz + 1);
+    float v110 = __ldg(p + sz + sy), v111 = __ldg(p + sz + sy + 1);
+    float a0 = lerp32(v000, v001, x.f, x.omf);
+    float a1 = lerp32(v010, v011, x.f, x.omf);
+    float a2 = lerp32(v100, v101, x.f, x.omf);
+    float a3 = lerp32(v110, v111, x.f, x.omf);
+    float b0 = lerp32(a0, a1, y.f, y.omf);
+    float b1 = lerp32(a2, a3, y.f, y.omf);
+    return lerp32(b0, b1, z.f, z.omf);
+}
+
+// sample_buffer (GPU_kernel.cu:43-62) for a field of x-extent nx, y-extent ny whose origin is
+// (ox,oy,oz) (= -0.5h on a staggered axis): p is the WORLD position.
+template <bool P2>
+__device__ __forceinline__ float sample(const float *__restrict__ b, int nx, int ny, const Grid3 &g,
+                                        float ox, float oy, float oz, float px, float py, float pz)
+{
+    Frac x = split<P2>(px - ox, g.h, g.inv_h);
+    Frac y = split<P2>(py - oy, g.h, g.inv_h);
+    Frac z = split<P2>(pz - oz, g.h, g.inv_h);
+    int sy = nx, sz = nx * ny;
+    return tri8(b + (x.i + sy * y.i + sz * z.i), sy, sz, x, y, z);
+}
+
+struct Vel3 {
+    const float *__restrict__ u;
+    const float *__restrict__ v;
+    const float *__restrict__ w;
+};
+
+// getVelocity (GPU_kernel.cu:64-72): the three staggered samples share the six distinct
+// (axis, offset) splits instead of computing nine.
+template <bool P2>
+__device__ __forceinline__ float3 get_velocity(const Vel3 &vel, const Grid3 &g, float px, float py,
+                                               float pz)
+{
+    const float hh = 0.5f * g.h;   // pos - (-0.5h)
+    Frac x0 = split<P2>(px, g.h, g.inv_h), x5 = split<P2>(px + hh, g.h, g.inv_h);
+    Frac y0 = split<P2>(py, g.h, g.inv_h), y5 = split<P2>(py + hh, g.h, g.inv_h);
+    Frac z0 = split<P2>(pz, g.h, g.inv_h), z5 = split<P2>(pz + hh, g.h, g.inv_h);
+    float3 r;
+    {
+        int sy = g.ni + 1, sz = (g.ni + 1) * g.nj;
+        r.x = tri8(vel.u + (x5.i + sy * y0.i + sz * z0.i), sy, sz, x5, y0, z0);
+    }
+    {
+        int sy = g.ni, sz = g.ni * (g.nj + 1);
+        r.y = tri8(vel.v + (x0.i + sy * y5.i + sz * z0.i), sy, sz, x0, y5, z0);
+    }
+    {
+        int sy = g.ni, sz = g.ni * g.nj;
+        r.z = tri8(vel.w + (x0.i + sy * y0.i + sz * z5.i), sy, sz, x0, y0, z5);
+    }
+    return r;
+}
+
+// traceRK3 (GPU_kernel.cu:74-90): Ralston RK3 with the reference's clamp band [h,(n-1)h].
+// c1,c2,c3 are rounded from double like the reference; the midpoints use one fused
+// multiply-add each (the reference forms them in double and rounds once).
+template <bool P2>
+__device__ __forceinline__ float3 trace_rk3(const Vel3 &vel, const Grid3 &g, float dt, float3 p)
+{
+    const float c1 = (float)(2.0 / 9.0 * (double)dt);
+    const float c2 = (float)(3.0 / 9.0 * (double)dt);
+    const float c3 = (float)(4.0 / 9.0 * (double)dt);
+    const float hd = 0.5f * dt;
+    const float qd = (float)(0.75 * (double)dt);
+    float3 v1 = get_velocity<P2>(vel, g, p.x, p.y, p.z);
+    float3 v2 = get_velocity<P2>(vel, g, fmaf(hd, v1.x, p.x), fmaf(hd, v1.y, p.y), fmaf(hd, v1.z, p.z));
+    float3 v3 = get_velocity<P2>(vel, g, fmaf(qd, v2.x, p.x), fmaf(qd, v2.y, p.y), fmaf(qd, v2.z, p.z));
+    float3 o;
+    o.x = fmaf(c3, v3.x, fmaf(c2, v2.x, fmaf(c1, v1.x, p.x)));
+    o.y = fmaf(c3, v3.y, fmaf(c2, v2.y, fmaf(c1, v1.y, p.y)));
+    o.z = fmaf(c3, v3.z, fmaf(c2, v2.z, fmaf(c1, v1.z, p.z)));
+    o.x = clampf(o.x, g.h, (float)g.ni * g.h - g.h);
+    o.y = clampf(o.y, g.h, (float)g.nj * g.h - g.h);
+    o.z = clampf(o.z, g.h, (float)g.nk * g.h - g.h);
+    return o;
+}
+
+// trace (GPU_kernel.cu:92-125): sub-steps of cfldt until |dt| is covered; the float loop is the
+// reference's, so every thread takes the same sub-step sequence as the reference does.
+template <bool P2>
+__device__ __forceinline__ float3 trace(const Vel3 &vel, const Grid3 &g, float cfldt, float dt, float3 p)
+{
+    const float sgn = dt > 0.f ? 1.0f : -1.0f;
+    const float T = fabsf(dt);
+    float t = 0.f, sub = cfldt;
+    while (t < T) {
+        if (t + sub > T) sub = T - t;
+        p = trace_rk3<P2>(vel, g, sgn * sub, p);
+        t += sub;
+    }
+    return p;
+}
+
+// Three co-located map components sampled at one world position (the maps are cell-centred
+// arrays of the global grid with origin 0): one split, 24 loads.
+struct Map3 {
+    const float *__restrict__ x;
+    const float *__restrict__ y;
+    const float *__restrict__ z;
+};
+
+template <bool P2>
+__device__ __forceinline__ float3 sample_map(const Map3 &m, const Grid3 &g, float px, float py, float pz)
+{
+    Frac x = split<P2>(px, g.h, g.inv_h);
+    Frac y = split<P2>(py, g.h, g.inv_h);
+    Frac z = split<P2>(pz, g.h, g.inv_h);
+    int sy = g.ni, sz = g.ni * g.nj;
+    int o = x.i + sy * y.i + sz * z.i;
+    float3 r;
+    r.x = tri8(m.x + o, sy, sz, x, y, z);
+    r.y = tri8(m.y + o, sy, sz, x, y, z);
+    r.z = tri8(m.z + o, sy, sz, x, y, z);
+    return r;
+}
+
+// NF co-located fields (same staggering) sampled at one world position: one split.
+template <bool P2, int NF>
+__device__ __forceinline__ void sample_fields(const float *const (&src)[NF], int nx, int ny,
+                                              const Grid3 &g, float ox, float oy, float oz, float px,
+                                              float py, float pz, float (&out)[NF])
+{
+    Frac x = split<P2>(px - ox, g.h, g.inv_h);
+    Frac y = split<P2>(py - oy, g.h, g.inv_h);
+    Frac z = split<P2>(pz - oz, g.h, g.inv_h);
+    int sy = nx, sz = nx * ny;
+    int o = x.i + sy * y.i + sz * z.i;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out[f] = tri8(src[f] + o, sy, sz, x, y, z);
+}
+
+// The quadrature shared by advect / compensate / cumulate (GPU_kernel.cu:317-371): eight
+// sub-cell points at +-h/4 (or one point when is_point) plus the centre.  For every point:
+// sample the map, clamp to [lo,hi], sample NS co-located source fields there.  Returns
+//   sum[f]   = sum_ii wgt[f] * src_f(map(c + off_ii))   accumulated in the reference's order
+//   value[f] = src_f(map(c))
+template <bool P2, int NS>
+__device__ __forceinline__ void quad_gather(const Map3 &m, const Grid3 &g, float cx, float cy, float cz,
+                                            float lo, float hix, float hiy, float hiz,
+                                            const float *const (&src)[NS], int fnx, int fny, float ox,
+                                            float oy, float oz, bool is_point, const float (&wgt)[NS],
+                                            float (&sum)[NS], float (&value)[NS])
+{
+#pragma unroll
+    for (int f = 0; f < NS; ++f) sum[f] = 0.f;
+    const float q = 0.25f * g.h;
+    const int ev = is_point ? 1 : 8;
+    for (int ii = 0; ii < ev; ++ii) {
+        // offsets in the reference's order: x sign = bit 2, y sign = bit 1, z sign = bit 0
+        float dx = is_point ? 0.f : ((ii & 4) ? -q : q);
+        float dy = is_point ? 0.f : ((ii & 2) ? -q : q);
+        float dz = is_point ? 0.f : ((ii & 1) ? -q : q);
+        float3 mp = sample_map<P2>(m, g, cx + dx, cy + dy, cz + dz);
+        mp.x = clampf(mp.x, lo, hix);
+        mp.y = clampf(mp.y, lo, hiy);
+        mp.z = clampf(mp.z, lo, hiz);
+        float s[NS];
+        sample_fields<P2, NS>(src, fnx, fny, g, ox, oy, oz, mp.x, mp.y, mp.z, s);
+#pragma unroll
+        for (int f = 0; f < NS; ++f) sum[f] = fmaf(wgt[f], s[f], sum[f]);
+    }
+    float3 mp = sample_map<P2>(m, g, cx, cy, cz);
+    mp.x = clampf(mp.x, lo, hix);
+    mp.y = clampf(mp.y, lo, hiy);
+    mp.z = clampf(mp.z, lo, hiz);
+    sample_fields<P2, NS>(src, fnx, fny, g, ox, oy, oz, mp.x, mp.y, mp.z, value);
+}
+
+// ---- reductions -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide max of non-negative floats, then one atomicMax per block on the int pattern
+// (valid because the values are >= 0).
+__device__ __forceinline__ void block_atomic_max(float v, float *dst)
+{
+    __shared__ float smax[32];
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    v = warp_max(v);
+    if ((tid & 31) == 0) smax[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        float r = tid < (nthreads + 31) / 32 ? smax[tid] : 0.f;
+        r = warp_max(r);
+        if (tid == 0 && r > 0.f) atomicMax(reinterpret_cast<int *>(dst), __float_as_int(r));
+    }
+}
+
+}  // namespace bmq

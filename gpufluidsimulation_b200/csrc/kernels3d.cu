@@ -1,0 +1,671 @@
+// 3D BiMocq^2 advection kernels for sm_100a and their host launchers.
+//
+// Every kernel works on GLOBAL indices: field pointers are "virtual bases" (pointer to plane 0
+// of the global grid, which for a z-slab rank is its local pointer minus first_plane*nx*ny) and
+// the launch covers global planes [kbeg,kend).  Interior guards are the reference's, in global
+// indices, so a slab rank computes exactly the values a single GPU would.
+//
+// Thread mapping: blockDim = (32, 8, 1); x -> i (coalesced rows), y -> j, blockIdx.z -> k.
+// No integer div/mod per thread (the reference decodes a flat index with two of each).
+#include "launch3d.h"
+#include "device3d.cuh"
+
+#include <atomic>
+
+namespace bmq {
+
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long kernel_launch_count() { return g_launches.load(); }
+static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static inline bool is_pow2_h(const Grid3 &g)
+{
+    int e;
+    float m = frexpf(g.h, &e);
+    // i*h, i*h +- h/4, +- h/2 must all be exact: (4*n+4) < 2^24
+    int nmax = g.ni > g.nj ? g.ni : g.nj;
+    nmax = nmax > g.nk ? nmax : g.nk;
+    return m == 0.5f && (long long)nmax * 4 + 8 < (1ll << 24);
+}
+
+Grid3 make_grid(int ni, int nj, int nk, float h)
+{
+    Grid3 g;
+    g.ni = ni; g.nj = nj; g.nk = nk; g.h = h; g.inv_h = 1.0f / h;
+    return g;
+}
+
+static inline dim3 block3() { return dim3(32, 8, 1); }
+static inline dim3 grid3(int fi, int fj, KRange r)
+{
+    return dim3((fi + 31) / 32, (fj + 7) / 8, r.kend - r.kbeg);
+}
+
+#define BMQ_IJK(fi, fj)                                          \
+    const int i = blockIdx.x * 32 + threadIdx.x;                 \
+    const int j = blockIdx.y * 8 + threadIdx.y;                  \
+    const int k = kbeg + blockIdx.z;                             \
+    if (i >= (fi) || j >= (fj)) return;
+
+// ------------------------------------------------------------------ forward map (a4)
+// forward_kernel, GPU_kernel.cu:127-144: psi <- trace(psi, +dt) in place, NMAP mappers at once
+// (each mapper's particle is independent; tracing two per thread doubles the loads in flight).
+template <bool P2, int NMAP>
+__global__ void __launch_bounds__(256)
+k_forward(Grid3 g, int kbeg, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
+{
+    BMQ_IJK(g.ni, g.nj)
+    if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
+    const int idx = i + g.ni * (j + g.nj * k);
+#pragma unroll
+    for (int m = 0; m < NMAP; ++m) {
+        float3 p = make_float3(maps.x[m][idx], maps.y[m][idx], maps.z[m][idx]);
+        p = trace<P2>(vel, g, cfldt, dt, p);
+        maps.x[m][idx] = p.x;
+        maps.y[m][idx] = p.y;
+        maps.z[m][idx] = p.z;
+    }
+}
+
+// ------------------------------------------------------------------ DMC backward sub-step (a5)
+// DMC_backward_kernel, GPU_kernel.cu:169-204.  The back-traced point depends only on the cell
+// and the velocity, so both mappers (velocity + scalar) are updated from one evaluation.
+__device__ __forceinline__ float dmc_axis(float p, float v, float a, float s)
+{
+    // (fabs(a) > 1e-4) is a float-vs-double comparison in the reference
+    if ((double)fabsf(a) > 1e-4) return p - (1.f - expf(-a * s)) * v / a;
+    return fmaf(-v, s, p);
+}
+
+template <bool P2, int NMAP>
+__global__ void __launch_bounds__(256)
+k_dmc(Grid3 g, int kbeg, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
+{
+    BMQ_IJK(g.ni, g.nj)
+    if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
+    const int idx = i + g.ni * (j + g.nj * k);
+    const float h = g.h;
+    const float px = h * (float)i, py = h * (float)j, pz = h * (float)k;
+    float3 v0 = get_velocity<P2>(vel, g, px, py, pz);
+    const float tx = v0.x > 0.f ? px - h : px + h;
+    const float ty = v0.y > 0.f ? py - h : py + h;
+    const float tz = v0.z > 0.f ? pz - h : pz + h;
+    float3 v1 = get_velocity<P2>(vel, g, tx, ty, tz);
+    const float ax = (v0.x - v1.x) / (px - tx);
+    const float ay = (v0.y - v1.y) / (py - ty);
+    const float az = (v0.z - v1.z) / (pz - tz);
+    const float nx = dmc_axis(px, v0.x, ax, substep);
+    const float ny = dmc_axis(py, v0.y, ay, substep);
+    const float nz = dmc_axis(pz, v0.z, az, substep);
+    Frac fx = split<P2>(nx, g.h, g.inv_h), fy = split<P2>(ny, g.h, g.inv_h), fz = split<P2>(nz, g.h, g.inv_h);
+    const int sy = g.ni, sz = g.ni * g.nj;
+    const int o = fx.i + sy * fy.i + sz * fz.i;
+#pragma unroll
+    for (int m = 0; m < NMAP; ++m) {
+        out.x[m][idx] = tri8(in.x[m] + o, sy, sz, fx, fy, fz);
+        out.y[m][idx] = tri8(in.y[m] + o, sy, sz, fx, fy, fz);
+        out.z[m][idx] = tri8(in.z[m] + o, sy, sz, fx, fy, fz);
+    }
+}
+
+// ------------------------------------------------------------------ semi-Lagrangian (a12)
+// semilag_kernel, GPU_kernel.cu:206-233; NF co-located fields share one back-trace.
+template <bool P2, int NF>
+__global__ void __launch_bounds__(256)
+k_semilag(Grid3 g, int kbeg, Vel3 vel, Stag st, FieldSetRW<NF> out, FieldSetRO<NF> src, float cfldt, float dt)
+{
+    const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
+    BMQ_IJK(fi, fj)
+    if (!(i > 1 && i < fi - 2 - st.dx && j > 1 && j < fj - 2 - st.dy && k > 1 && k < fk - 2 - st.dz)) return;
+    const float ox = -(float)st.dx * 0.5f * g.h, oy = -(float)st.dy * 0.5f * g.h, oz = -(float)st.dz * 0.5f * g.h;
+    float3 p = make_float3(fmaf(g.h, (float)i, ox), fmaf(g.h, (float)j, oy), fmaf(g.h, (float)k, oz));
+    p = trace<P2>(vel, g, cfldt, dt, p);
+    float s[NF];
+    sample_fields<P2, NF>(src.p, fi, fj, g, ox, oy, oz, p.x, p.y, p.z, s);
+    const int idx = i + fi * (j + fj * k);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out.p[f][idx] = s[f];
+}
+
+// ------------------------------------------------------------------ advect (a6)
+// advect_kernel, GPU_kernel.cu:312-374: f = 1/2 * sum_8 1/8 f0(clamp(chi(x+d))) + 1/2 f0(clamp(chi(x)))
+template <bool P2, int NF>
+__global__ void __launch_bounds__(256)
+k_advect(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
+{
+    const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
+    BMQ_IJK(fi, fj)
+    if (!(2 + st.dx < i && i < fi - 3 && 2 + st.dy < j && j < fj - 3 && 2 + st.dz < k && k < fk - 3)) return;
+    const float h = g.h;
+    const float ox = -(float)st.dx * 0.5f * h, oy = -(float)st.dy * 0.5f * h, oz = -(float)st.dz * 0.5f * h;
+    const float cx = fmaf(h, (float)i, ox), cy = fmaf(h, (float)j, oy), cz = fmaf(h, (float)k, oz);
+    float sum[NF], val[NF], wgt[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) wgt[f] = is_point ? 1.0f : 0.125f;
+    quad_gather<P2, NF>(chi, g, cx, cy, cz, h, h * (float)g.ni - h, h * (float)g.nj - h, h * (float)g.nk - h,
+                        init.p, fi, fj, ox, oy, oz, is_point, wgt, sum, val);
+    const int idx = i + fi * (j + fj * k);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out.p[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]);
+}
+
+// ------------------------------------------------------------------ time-0 error (a7, first kernel)
+// compensate_kernel, GPU_kernel.cu:438-499: e0 = quad9[f(clamp0(psi(x+d)))] - f_init
+template <bool P2, int NF>
+__global__ void __launch_bounds__(256)
+k_error(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
+{
+    const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
+    BMQ_IJK(fi, fj)
+    if (!(1 + st.dx < i && i < fi - 2 && 1 + st.dy < j && j < fj - 2 && 1 + st.dz < k && k < fk - 2)) return;
+    const float h = g.h;
+    const float ox = -(float)st.dx * 0.5f * h, oy = -(float)st.dy * 0.5f * h, oz = -(float)st.dz * 0.5f * h;
+    const float cx = fmaf(h, (float)i, ox), cy = fmaf(h, (float)j, oy), cz = fmaf(h, (float)k, oz);
+    float sum[NF], val[NF], wgt[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) wgt[f] = is_point ? 1.0f : 0.125f;
+    quad_gather<P2, NF>(psi, g, cx, cy, cz, 0.f, h * (float)g.ni, h * (float)g.nj, h * (float)g.nk,
+                        src.p, fi, fj, ox, oy, oz, is_point, wgt, sum, val);
+    const int idx = i + fi * (j + fj * k);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) e0.p[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]) - __ldg(init.p[f] + idx);
+}
+
+// ------------------------------------------------------------------ accumulate (a9)
+// cumulate_kernel, GPU_kernel.cu:376-436: target += coeff * quad9[d(clamp0(map(x+d)))].
+// NCH change sets (external forces, projection) are gathered through the same map in one pass
+// and added in the reference's call order, (target + s0) + s1, so the result is the one two
+// consecutive launches give.
+template <bool P2, int NF, int NCH>
+__global__ void __launch_bounds__(256)
+k_cumulate(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change,
+           Coeffs<NCH> coeff, Map3 map)
+{
+    const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
+    BMQ_IJK(fi, fj)
+    if (!(1 + st.dx < i && i < fi - 2 && 1 + st.dy < j && j < fj - 2 && 1 + st.dz < k && k < fk - 2)) return;
+    const float h = g.h;
+    const float ox = -(float)st.dx * 0.5f * h, oy = -(float)st.dy * 0.5f * h, oz = -(float)st.dz * 0.5f * h;
+    const float cx = fmaf(h, (float)i, ox), cy = fmaf(h, (float)j, oy), cz = fmaf(h, (float)k, oz);
+    float sum[NF * NCH], val[NF * NCH], wgt[NF * NCH];
+    // the reference accumulates weight*coeff*sample (GPU_kernel.cu:420): one weight per change set
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) wgt[c * NF + f] = (is_point ? 1.0f : 0.125f) * coeff.c[c];
+    quad_gather<P2, NF * NCH>(map, g, cx, cy, cz, 0.f, h * (float)g.ni, h * (float)g.nj, h * (float)g.nk,
+                              change.p, fi, fj, ox, oy, oz, is_point, wgt, sum, val);
+    const int idx = i + fi * (j + fj * k);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        float t = target.p[f][idx];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const float v = coeff.c[c] * val[c * NF + f];
+            t += fmaf(0.5f, sum[c * NF + f], 0.5f * v);
+        }
+        target.p[f][idx] = t;
+    }
+}
+
+// ------------------------------------------------------------------ apply correction + clamp (a7)
+// cumulate_kernel(coeff=-0.5) followed by clampExtrema_kernel (GPU_kernel.cu:659-665, 146-167)
+// in one pass: out = clamp(f_adv - 1/2 quad9[e0(clamp0(chi(x+d)))], min27(f_adv), max27(f_adv)).
+// Writes every cell of the plane (out = f_adv where the reference leaves f_adv untouched), so
+// out may be a different buffer than f_adv and no device-to-device copy is needed.
+template <bool P2, int NF>
+__global__ void __launch_bounds__(256)
+k_apply_clamp(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, FieldSetRO<NF> fadv,
+              FieldSetRO<NF> e0, Map3 chi)
+{
+    const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
+    BMQ_IJK(fi, fj)
+    const int idx = i + fi * (j + fj * k);
+    float r[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) r[f] = __ldg(fadv.p[f] + idx);
+    if (1 + st.dx < i && i < fi - 2 && 1 + st.dy < j && j < fj - 2 && 1 + st.dz < k && k < fk - 2) {
+        const float h = g.h;
+        const float ox = -(float)st.dx * 0.5f * h, oy = -(float)st.dy * 0.5f * h, oz = -(float)st.dz * 0.5f * h;
+        const float cx = fmaf(h, (float)i, ox), cy = fmaf(h, (float)j, oy), cz = fmaf(h, (float)k, oz);
+        float sum[NF], val[NF], wgt[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) wgt[f] = (is_point ? 1.0f : 0.125f) * -0.5f;
+        quad_gather<P2, NF>(chi, g, cx, cy, cz, 0.f, h * (float)g.ni, h * (float)g.nj, h * (float)g.nk,
+                            e0.p, fi, fj, ox, oy, oz, is_point, wgt, sum, val);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) r[f] += fmaf(0.5f, sum[f], 0.5f * (-0.5f * val[f]));
+    }
+    if (i > 0 && i < fi - 1 && j > 0 && j < fj - 1 && k > 0 && k < fk - 1) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const float *b = fadv.p[f];
+            float mx = __ldg(b + idx), mn = mx;
+#pragma unroll
+            for (int kk = -1; kk <= 1; ++kk)
+#pragma unroll
+                for (int jj = -1; jj <= 1; ++jj)
+#pragma unroll
+                    for (int ii = -1; ii <= 1; ++ii) {
+                        const float v = __ldg(b + idx + ii + fi * (jj + fj * kk));
+                        mx = fmaxf(mx, v);
+                        mn = fminf(mn, v);
+                    }
+            r[f] = fminf(fmaxf(mn, r[f]), mx);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out.p[f][idx] = r[f];
+}
+
+// clampExtrema_kernel alone (legacy gpu_compensate_* keeps the reference's buffer contract)
+__global__ void __launch_bounds__(256)
+k_clamp_extrema(int fi, int fj, int fk, int kbeg, const float *__restrict__ before, float *after)
+{
+    BMQ_IJK(fi, fj)
+    if (!(i > 0 && i < fi - 1 && j > 0 && j < fj - 1 && k > 0 && k < fk - 1)) return;
+    const int idx = i + fi * (j + fj * k);
+    float mx = __ldg(before + idx), mn = mx;
+#pragma unroll
+    for (int kk = -1; kk <= 1; ++kk)
+#pragma unroll
+        for (int jj = -1; jj <= 1; ++jj)
+#pragma unroll
+            for (int ii = -1; ii <= 1; ++ii) {
+                const float v = __ldg(before + idx + ii + fi * (jj + fj * kk));
+                mx = fmaxf(mx, v);
+                mn = fminf(mn, v);
+            }
+    after[idx] = fminf(fmaxf(mn, after[idx]), mx);
+}
+
+// ------------------------------------------------------------------ two-level blend (a8)
+// doubleAdvect_kernel, GPU_kernel.cu:236-310
+template <bool P2, int NF>
+__global__ void __launch_bounds__(256)
+k_double_advect(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> field, FieldSetRO<NF> prev,
+                Map3 chi, Map3 chip, float blend)
+{
+    const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
+    BMQ_IJK(fi, fj)
+    if (!(2 + st.dx < i && i < fi - 3 && 2 + st.dy < j && j < fj - 3 && 2 + st.dz < k && k < fk - 3)) return;
+    const float h = g.h;
+    const float ox = -(float)st.dx * 0.5f * h, oy = -(float)st.dy * 0.5f * h, oz = -(float)st.dz * 0.5f * h;
+    const float cx = fmaf(h, (float)i, ox), cy = fmaf(h, (float)j, oy), cz = fmaf(h, (float)k, oz);
+    const float hix = h * (float)g.ni - h, hiy = h * (float)g.nj - h, hiz = h * (float)g.nk - h;
+    const float q = 0.25f * h;
+    const int ev = is_point ? 1 : 8;
+    const float wgt = is_point ? 1.0f : 0.125f;
+    float sum[NF], val[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) sum[f] = 0.f;
+    for (int ii = 0; ii <= ev; ++ii) {
+        const bool centre = ii == ev;
+        const float dx = (centre || is_point) ? 0.f : ((ii & 4) ? -q : q);
+        const float dy = (centre || is_point) ? 0.f : ((ii & 2) ? -q : q);
+        const float dz = (centre || is_point) ? 0.f : ((ii & 1) ? -q : q);
+        float3 mid = sample_map<P2>(chi, g, cx + dx, cy + dy, cz + dz);
+        mid.x = clampf(mid.x, h, hix); mid.y = clampf(mid.y, h, hiy); mid.z = clampf(mid.z, h, hiz);
+        float3 fin = sample_map<P2>(chip, g, mid.x, mid.y, mid.z);
+        fin.x = clampf(fin.x, h, hix); fin.y = clampf(fin.y, h, hiy); fin.z = clampf(fin.z, h, hiz);
+        float s[NF];
+        sample_fields<P2, NF>(prev.p, fi, fj, g, ox, oy, oz, fin.x, fin.y, fin.z, s);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            if (centre) val[f] = s[f];
+            else sum[f] = fmaf(wgt, s[f], sum[f]);
+        }
+    }
+    const int idx = i + fi * (j + fj * k);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const float pv = 0.5f * (sum[f] + val[f]);
+        field.p[f][idx] = fmaf(field.p[f][idx], blend, (1.f - blend) * pv);
+    }
+}
+
+// ------------------------------------------------------------------ distortion (a10) + reductions
+// estimate_kernel, GPU_kernel.cu:501-537, for NMAP mappers, with the max-reduction the
+// reference does on the host (Mapping.cpp:100-117) fused in: warp shuffle -> block -> one
+// atomicMax per block.  Also reduces max |map_z - z| (in world units) for halo sizing.
+template <bool P2, int NMAP>
+__global__ void __launch_bounds__(256)
+k_estimate(Grid3 g, int kbeg, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
+           const signed char *__restrict__ boundary)
+{
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    const int j = blockIdx.y * 8 + threadIdx.y;
+    const int k = kbeg + blockIdx.z;
+    float d2[NMAP], dispz = 0.f;
+#pragma unroll
+    for (int m = 0; m < NMAP; ++m) d2[m] = 0.f;
+    const bool inside = i < g.ni && j < g.nj;
+    if (inside && i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2) {
+        const int idx = i + g.ni * (j + g.nj * k);
+        const float px = g.h * (float)i, py = g.h * (float)j, pz = g.h * (float)k;
+        const bool counted = boundary == nullptr || boundary[idx] != 2;
+#pragma unroll
+        for (int m = 0; m < NMAP; ++m) {
+            Map3 B{bwd.x[m], bwd.y[m], bwd.z[m]}, F{fwd.x[m], fwd.y[m], fwd.z[m]};
+            float3 b = sample_map<P2>(B, g, px, py, pz);
+            float3 f = sample_map<P2>(F, g, b.x, b.y, b.z);
+            const float dbf = (px - f.x) * (px - f.x) + (py - f.y) * (py - f.y) + (pz - f.z) * (pz - f.z);
+            float3 f2 = sample_map<P2>(F, g, px, py, pz);
+            float3 b2 = sample_map<P2>(B, g, f2.x, f2.y, f2.z);
+            const float dfb = (px - b2.x) * (px - b2.x) + (py - b2.y) * (py - b2.y) + (pz - b2.z) * (pz - b2.z);
+            const float d = fmaxf(dbf, dfb);
+            if (outp.dist[m]) outp.dist[m][idx] = d;
+            if (counted) d2[m] = d;
+            dispz = fmaxf(dispz, fmaxf(fabsf(b.z - pz), fabsf(f2.z - pz)));
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NMAP; ++m) {
+        if (outp.d2max[m]) block_atomic_max(d2[m], outp.d2max[m]);
+        __syncthreads();
+    }
+    if (outp.dispz) block_atomic_max(dispz, outp.dispz);
+}
+
+// max |x| over up to three arrays (getCFL, BimocqSolver.cpp:1093-1117), grid-stride, float4 loads
+__global__ void __launch_bounds__(256)
+k_maxabs3(const float *__restrict__ a, size_t na, const float *__restrict__ b, size_t nb,
+          const float *__restrict__ c, size_t nc, float *out)
+{
+    float m = 0.f;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float *arr[3] = {a, b, c};
+    const size_t len[3] = {na, nb, nc};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float *p = arr[q];
+        if (!p) continue;
+        const size_t n = len[q];
+        // head to 16-byte alignment, vector body, tail
+        size_t head = ((16 - ((uintptr_t)p & 15)) & 15) / 4;
+        if (head > n) head = n;
+        for (size_t e = tid; e < head; e += stride) m = fmaxf(m, fabsf(__ldg(p + e)));
+        const float4 *p4 = reinterpret_cast<const float4 *>(p + head);
+        const size_t n4 = (n - head) / 4;
+        for (size_t e = tid; e < n4; e += stride) {
+            const float4 v = __ldg(p4 + e);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        for (size_t e = head + n4 * 4 + tid; e < n; e += stride) m = fmaxf(m, fabsf(__ldg(p + e)));
+    }
+    block_atomic_max(m, out);
+}
+
+// a[i] += c*b[i]  (add_kernel, GPU_kernel.cu:560-565, with the missing bounds check) and
+// out[i] = a[i] + c*b[i] (add_field_kernel, :878-883)
+__global__ void __launch_bounds__(256) k_axpy(float *a, const float *__restrict__ b, float c, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) a[e] = fmaf(c, b[e], a[e]);
+}
+__global__ void __launch_bounds__(256)
+k_add_field(float *out, const float *__restrict__ a, const float *__restrict__ b, float c, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) out[e] = fmaf(c, b[e], a[e]);
+}
+
+// identity maps x = i*h (Mapping.cpp:310-324) for up to two mappers x (psi, chi)
+__global__ void __launch_bounds__(256) k_identity(Grid3 g, int kbeg, IdentityOut o)
+{
+    BMQ_IJK(g.ni, g.nj)
+    const int idx = i + g.ni * (j + g.nj * k);
+    const float x = (float)i * g.h, y = (float)j * g.h, z = (float)k * g.h;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (o.x[m]) { o.x[m][idx] = x; o.y[m][idx] = y; o.z[m][idx] = z; }
+    }
+}
+
+// ================================================================== host launchers
+#define DISPATCH_P2(g, CALL_T, CALL_F) do { if (is_pow2_h(g)) { CALL_T; } else { CALL_F; } } while (0)
+
+cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float *u, const float *v,
+                           const float *w, int nmap, float *const maps[][3], float cfldt, float dt)
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Vel3 vel{u, v, w};
+    dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
+    if (nmap == 1) {
+        MapSetRW<1> m; m.x[0] = maps[0][0]; m.y[0] = maps[0][1]; m.z[0] = maps[0][2];
+        DISPATCH_P2(g, (k_forward<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)),
+                    (k_forward<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)));
+    } else {
+        MapSetRW<2> m;
+        for (int q = 0; q < 2; ++q) { m.x[q] = maps[q][0]; m.y[q] = maps[q][1]; m.z[q] = maps[q][2]; }
+        DISPATCH_P2(g, (k_forward<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)),
+                    (k_forward<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)));
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u, const float *v,
+                       const float *w, int nmap, const float *const in[][3], float *const out[][3],
+                       float substep)
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Vel3 vel{u, v, w};
+    dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
+    if (nmap == 1) {
+        MapSetRO<1> a; MapSetRW<1> b;
+        a.x[0] = in[0][0]; a.y[0] = in[0][1]; a.z[0] = in[0][2];
+        b.x[0] = out[0][0]; b.y[0] = out[0][1]; b.z[0] = out[0][2];
+        DISPATCH_P2(g, (k_dmc<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)),
+                    (k_dmc<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)));
+    } else {
+        MapSetRO<2> a; MapSetRW<2> b;
+        for (int q = 0; q < 2; ++q) {
+            a.x[q] = in[q][0]; a.y[q] = in[q][1]; a.z[q] = in[q][2];
+            b.x[q] = out[q][0]; b.y[q] = out[q][1]; b.z[q] = out[q][2];
+        }
+        DISPATCH_P2(g, (k_dmc<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)),
+                    (k_dmc<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)));
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int NF> static FieldSetRO<NF> ro(const float *const *p) { FieldSetRO<NF> f; for (int q = 0; q < NF; ++q) f.p[q] = p[q]; return f; }
+template <int NF> static FieldSetRW<NF> rw(float *const *p) { FieldSetRW<NF> f; for (int q = 0; q < NF; ++q) f.p[q] = p[q]; return f; }
+
+cudaError_t launch_semilag(cudaStream_t s, const Grid3 &g, KRange r, Stag st, const float *u,
+                           const float *v, const float *w, int nf, float *const *out,
+                           const float *const *src, float cfldt, float dt)
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Vel3 vel{u, v, w};
+    dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (nf == 1)
+        DISPATCH_P2(g, (k_semilag<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<1>(out), ro<1>(src), cfldt, dt)),
+                    (k_semilag<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<1>(out), ro<1>(src), cfldt, dt)));
+    else
+        DISPATCH_P2(g, (k_semilag<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<2>(out), ro<2>(src), cfldt, dt)),
+                    (k_semilag<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<2>(out), ro<2>(src), cfldt, dt)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
+                          float *const *out, const float *const *init, const float *const chi[3])
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Map3 m{chi[0], chi[1], chi[2]};
+    dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (nf == 1)
+        DISPATCH_P2(g, (k_advect<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(init), m)),
+                    (k_advect<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(init), m)));
+    else
+        DISPATCH_P2(g, (k_advect<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(init), m)),
+                    (k_advect<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(init), m)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_error(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
+                         float *const *e0, const float *const *src, const float *const *init,
+                         const float *const psi[3])
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Map3 m{psi[0], psi[1], psi[2]};
+    dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (nf == 1)
+        DISPATCH_P2(g, (k_error<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)),
+                    (k_error<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)));
+    else
+        DISPATCH_P2(g, (k_error<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(e0), ro<2>(src), ro<2>(init), m)),
+                    (k_error<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(e0), ro<2>(src), ro<2>(init), m)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cumulate(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
+                            int nch, float *const *target, const float *const *change,
+                            const float *coeff, const float *const map[3])
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Map3 m{map[0], map[1], map[2]};
+    dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+#define CUM(NF, NCH)                                                                                   \
+    {                                                                                                  \
+        Coeffs<NCH> c;                                                                                 \
+        for (int q = 0; q < NCH; ++q) c.c[q] = coeff[q];                                               \
+        DISPATCH_P2(g, (k_cumulate<true, NF, NCH><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<NF>(target), ro<NF * NCH>(change), c, m)), \
+                    (k_cumulate<false, NF, NCH><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<NF>(target), ro<NF * NCH>(change), c, m))); \
+    }
+    if (nf == 1 && nch == 1) CUM(1, 1)
+    else if (nf == 1 && nch == 2) CUM(1, 2)
+    else if (nf == 2 && nch == 1) CUM(2, 1)
+    else return cudaErrorInvalidValue;
+#undef CUM
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply_clamp(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
+                               float *const *out, const float *const *fadv, const float *const *e0,
+                               const float *const chi[3])
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Map3 m{chi[0], chi[1], chi[2]};
+    dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (nf == 1)
+        DISPATCH_P2(g, (k_apply_clamp<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)),
+                    (k_apply_clamp<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)));
+    else
+        DISPATCH_P2(g, (k_apply_clamp<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(fadv), ro<2>(e0), m)),
+                    (k_apply_clamp<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(fadv), ro<2>(e0), m)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_clamp_extrema(cudaStream_t s, int fi, int fj, int fk, KRange r, const float *before,
+                                 float *after)
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    k_clamp_extrema<<<grid3(fi, fj, r), block3(), 0, s>>>(fi, fj, fk, r.kbeg, before, after);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_double_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
+                                 float *const *field, const float *const *prev, const float *const chi[3],
+                                 const float *const chip[3], float blend)
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    Map3 m{chi[0], chi[1], chi[2]}, mp{chip[0], chip[1], chip[2]};
+    dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (nf == 1)
+        DISPATCH_P2(g, (k_double_advect<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(field), ro<1>(prev), m, mp, blend)),
+                    (k_double_advect<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(field), ro<1>(prev), m, mp, blend)));
+    else
+        DISPATCH_P2(g, (k_double_advect<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(field), ro<2>(prev), m, mp, blend)),
+                    (k_double_advect<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(field), ro<2>(prev), m, mp, blend)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, const float *const bwd[][3],
+                            const float *const fwd[][3], float *const *dist, float *const *d2max,
+                            float *dispz, const signed char *boundary)
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
+    if (nmap == 1) {
+        MapSetRO<1> b, f; DistOut<1> o;
+        b.x[0] = bwd[0][0]; b.y[0] = bwd[0][1]; b.z[0] = bwd[0][2];
+        f.x[0] = fwd[0][0]; f.y[0] = fwd[0][1]; f.z[0] = fwd[0][2];
+        o.dist[0] = dist ? dist[0] : nullptr; o.d2max[0] = d2max ? d2max[0] : nullptr; o.dispz = dispz;
+        DISPATCH_P2(g, (k_estimate<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)),
+                    (k_estimate<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)));
+    } else {
+        MapSetRO<2> b, f; DistOut<2> o;
+        for (int q = 0; q < 2; ++q) {
+            b.x[q] = bwd[q][0]; b.y[q] = bwd[q][1]; b.z[q] = bwd[q][2];
+            f.x[q] = fwd[q][0]; f.y[q] = fwd[q][1]; f.z[q] = fwd[q][2];
+            o.dist[q] = dist ? dist[q] : nullptr; o.d2max[q] = d2max ? d2max[q] : nullptr;
+        }
+        o.dispz = dispz;
+        DISPATCH_P2(g, (k_estimate<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)),
+                    (k_estimate<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)));
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+static int reduce_blocks(size_t n)
+{
+    size_t b = (n / 4 + 255) / 256;
+    const size_t cap = 148 * 8;   // 148 SMs x 8 resident 256-thread CTAs
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+cudaError_t launch_maxabs3(cudaStream_t s, const float *a, size_t na, const float *b, size_t nb,
+                           const float *c, size_t nc, float *out_dev)
+{
+    size_t n = na > nb ? na : nb;
+    n = n > nc ? n : nc;
+    k_maxabs3<<<reduce_blocks(n), 256, 0, s>>>(a, na, b, nb, c, nc, out_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_axpy(cudaStream_t s, float *a, const float *b, float c, size_t n)
+{
+    if (n == 0) return cudaSuccess;
+    k_axpy<<<reduce_blocks(n * 4), 256, 0, s>>>(a, b, c, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_add_field(cudaStream_t s, float *out, const float *a, const float *b, float c, size_t n)
+{
+    if (n == 0) return cudaSuccess;
+    k_add_field<<<reduce_blocks(n * 4), 256, 0, s>>>(out, a, b, c, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_identity(cudaStream_t s, const Grid3 &g, KRange r, int nsets, float *const sets[][3])
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    IdentityOut o;
+    for (int m = 0; m < 4; ++m) {
+        o.x[m] = m < nsets ? sets[m][0] : nullptr;
+        o.y[m] = m < nsets ? sets[m][1] : nullptr;
+        o.z[m] = m < nsets ? sets[m][2] : nullptr;
+    }
+    k_identity<<<grid3(g.ni, g.nj, r), block3(), 0, s>>>(g, r.kbeg, o);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace bmq

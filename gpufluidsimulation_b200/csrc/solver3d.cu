@@ -1,0 +1,683 @@
+// Handle API (bmq3d_*): device-resident BiMocq^2 advection state, the fused stage sequence and
+// the reinitialisation scheduler of BimocqSolver::advanceBimocq (bimocq3D/BimocqSolver.cpp:88-230)
+// with MapperBase semantics (bimocq3D/Mapping.cpp:7-271).
+//
+// Memory: every field is one cudaMalloc of its stored planes plus one plane + one row of zero
+// padding (the reference's trilinear sampler reads one node past the clamp bound with weight 0,
+// GPU_kernel.cu:53-61 with the clamps at :356/:419; the padding keeps those reads in bounds and
+// finite).  A z-slab rank stores planes [k_own0-halo, k_own1+halo+1) clipped to the field and
+// hands the kernels virtual base pointers, so all indices are global.
+//
+// Re-initialisation is pointer rotation: chi_prev <-> chi, f_prev <-> f_init, one identity fill
+// and one copy current -> init per field, instead of the reference's 15 full-field copies
+// (Mapping.cpp:430-447, BimocqSolver.cpp:1433-1451).
+#include "common.h"
+#include "launch3d.h"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <utility>
+#include <vector>
+
+using namespace bmq;
+
+namespace {
+
+enum { N_SCRATCH = 10, SCRATCH_BASE = 64, N_TMPMAP = 6 };
+
+struct Field {
+    float *alloc = nullptr;   // first stored plane
+    int nx = 0, ny = 0, nz = 0;   // full (global) dims of the field
+    int p0 = 0, p1 = 0;       // stored global planes [p0, p1)
+    size_t plane() const { return (size_t)nx * ny; }
+    size_t stored_elems() const { return plane() * (size_t)(p1 - p0); }
+    float *vbase() const { return alloc ? alloc - (ptrdiff_t)plane() * p0 : nullptr; }
+};
+
+}  // namespace
+
+struct bmq3d_solver {
+    int ni, nj, nk;
+    float h, blend;
+    int k0, k1, halo;          // owned planes [k0,k1), halo width
+    cudaStream_t stream = 0;
+    Grid3 g;
+    Field f[BMQ_F_COUNT];
+    Field scratch[N_SCRATCH];  // adv[5], err[5]
+    Field tmpmap[N_TMPMAP];    // DMC ping-pong: velocity chi xyz, scalar chi xyz
+    float *d_red = nullptr;    // device reduction scalars [8]
+    float *h_red = nullptr;    // pinned mirror
+    // scheduler state (BimocqSolver.h:142-143, Mapping.h:36)
+    int vel_last_reinit = 0, scalar_last_reinit = 0;
+    int vel_reinit_count = 0, scalar_reinit_count = 0;
+    float max_v = 0.f, cfldt = 0.f, proj_coeff = 2.f;
+    bool vel_reinit = false, scalar_reinit = false;
+    bmq3d_stats stats;
+    bool semi_alloc = false;
+};
+
+namespace {
+
+Stag stag_of(int id)
+{
+    switch (id) {
+    case BMQ_F_U: case BMQ_F_U_INIT: case BMQ_F_U_PREV: case BMQ_F_DU_EXT: case BMQ_F_DU_PROJ: case BMQ_F_U_SEMI:
+    case BMQ_F_U_ADV: case BMQ_F_U_ERR:
+        return Stag{1, 0, 0};
+    case BMQ_F_V: case BMQ_F_V_INIT: case BMQ_F_V_PREV: case BMQ_F_DV_EXT: case BMQ_F_DV_PROJ: case BMQ_F_V_SEMI:
+    case BMQ_F_V_ADV: case BMQ_F_V_ERR:
+        return Stag{0, 1, 0};
+    case BMQ_F_W: case BMQ_F_W_INIT: case BMQ_F_W_PREV: case BMQ_F_DW_EXT: case BMQ_F_DW_PROJ: case BMQ_F_W_SEMI:
+    case BMQ_F_W_ADV: case BMQ_F_W_ERR:
+        return Stag{0, 0, 1};
+    default:
+        return Stag{0, 0, 0};
+    }
+}
+
+int alloc_field(bmq3d_solver *s, Field &fd, Stag st)
+{
+    fd.nx = s->ni + st.dx;
+    fd.ny = s->nj + st.dy;
+    fd.nz = s->nk + st.dz;
+    fd.p0 = s->k0 - s->halo > 0 ? s->k0 - s->halo : 0;
+    fd.p1 = s->k1 + s->halo + 1 < fd.nz ? s->k1 + s->halo + 1 : fd.nz;
+    const size_t n = fd.stored_elems() + fd.plane() + fd.nx + 2;   // zero padding, see file header
+    BMQ_CK(cudaMalloc(&fd.alloc, n * sizeof(float)));
+    BMQ_CK(cudaMemsetAsync(fd.alloc, 0, n * sizeof(float), s->stream));
+    return BMQ_OK;
+}
+
+Field *field_of(bmq3d_solver *s, int id)
+{
+    if (id >= 0 && id < BMQ_F_COUNT) return &s->f[id];
+    if (id >= SCRATCH_BASE && id < SCRATCH_BASE + N_SCRATCH) return &s->scratch[id - SCRATCH_BASE];
+    return nullptr;
+}
+
+// owned compute range of a field with staggering dz: [k0,k1) plus the top face on the last slab
+KRange own(const bmq3d_solver *s, int dz) { return KRange{s->k0, s->k1 + ((dz && s->k1 == s->nk) ? 1 : 0)}; }
+// planes a whole-field fill should touch (everything stored)
+KRange stored(const Field &fd) { return KRange{fd.p0, fd.p1}; }
+
+int ensure_semi(bmq3d_solver *s)
+{
+    if (s->semi_alloc) return BMQ_OK;
+    for (int id = BMQ_F_U_SEMI; id <= BMQ_F_T_SEMI; ++id) {
+        int st = alloc_field(s, s->f[id], stag_of(id));
+        if (st != BMQ_OK) return st;
+    }
+    s->semi_alloc = true;
+    return BMQ_OK;
+}
+
+int identity_fill(bmq3d_solver *s, int first_id)
+{
+    float *const sets[1][3] = {{s->f[first_id].vbase(), s->f[first_id + 1].vbase(), s->f[first_id + 2].vbase()}};
+    BMQ_CK(launch_identity(s->stream, s->g, stored(s->f[first_id]), 1, sets));
+    return BMQ_OK;
+}
+int identity_fill_tmp(bmq3d_solver *s, int first)
+{
+    float *const sets[1][3] = {{s->tmpmap[first].vbase(), s->tmpmap[first + 1].vbase(), s->tmpmap[first + 2].vbase()}};
+    BMQ_CK(launch_identity(s->stream, s->g, stored(s->tmpmap[first]), 1, sets));
+    return BMQ_OK;
+}
+
+int copy_field(bmq3d_solver *s, Field &dst, const Field &src)
+{
+    BMQ_CK(cudaMemcpyAsync(dst.alloc, src.alloc, src.stored_elems() * sizeof(float), cudaMemcpyDeviceToDevice,
+                           s->stream));
+    return BMQ_OK;
+}
+
+// ---- stages ------------------------------------------------------------------------------
+
+int stage_maxvel(bmq3d_solver *s, float *out)
+{
+    BMQ_CK(cudaMemsetAsync(s->d_red, 0, sizeof(float), s->stream));
+    // owned planes only, so a slab's halo copies are not double counted (harmless for a max anyway)
+    const Field &u = s->f[BMQ_F_U], &v = s->f[BMQ_F_V], &w = s->f[BMQ_F_W];
+    KRange ru = own(s, 0), rw = own(s, 1);
+    BMQ_CK(launch_maxabs3(s->stream, u.vbase() + u.plane() * ru.kbeg, u.plane() * (ru.kend - ru.kbeg),
+                          v.vbase() + v.plane() * ru.kbeg, v.plane() * (ru.kend - ru.kbeg),
+                          w.vbase() + w.plane() * rw.kbeg, w.plane() * (rw.kend - rw.kbeg), s->d_red));
+    BMQ_CK(cudaMemcpyAsync(s->h_red, s->d_red, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    *out = s->h_red[0];
+    return BMQ_OK;
+}
+
+// getCFL (BimocqSolver.cpp:1093-1117) + the frame-0 rule (:94)
+void set_cfl(bmq3d_solver *s, int framenum, float max_abs)
+{
+    float mv = 1e-4f;
+    if (max_abs > mv) mv = max_abs;
+    s->cfldt = s->h / mv;
+    s->max_v = framenum == 0 ? s->h : mv;
+    s->stats.max_v = s->max_v;
+    s->stats.cfldt = s->cfldt;
+}
+
+int stage_dmc(bmq3d_solver *s, float substep)
+{
+    const float *const in[2][3] = {
+        {s->f[BMQ_F_VBWD_X].vbase(), s->f[BMQ_F_VBWD_Y].vbase(), s->f[BMQ_F_VBWD_Z].vbase()},
+        {s->f[BMQ_F_SBWD_X].vbase(), s->f[BMQ_F_SBWD_Y].vbase(), s->f[BMQ_F_SBWD_Z].vbase()}};
+    float *const out[2][3] = {{s->tmpmap[0].vbase(), s->tmpmap[1].vbase(), s->tmpmap[2].vbase()},
+                              {s->tmpmap[3].vbase(), s->tmpmap[4].vbase(), s->tmpmap[5].vbase()}};
+    BMQ_CK(launch_dmc(s->stream, s->g, own(s, 0), s->f[BMQ_F_U].vbase(), s->f[BMQ_F_V].vbase(),
+                      s->f[BMQ_F_W].vbase(), 2, in, out, substep));
+    // ping-pong instead of the reference's three device-to-device copies (GPU_Advection.h:466-468)
+    for (int c = 0; c < 3; ++c) {
+        std::swap(s->f[BMQ_F_VBWD_X + c], s->tmpmap[c]);
+        std::swap(s->f[BMQ_F_SBWD_X + c], s->tmpmap[3 + c]);
+    }
+    return BMQ_OK;
+}
+
+int stage_forward(bmq3d_solver *s, float dt)
+{
+    float *const maps[2][3] = {
+        {s->f[BMQ_F_VFWD_X].vbase(), s->f[BMQ_F_VFWD_Y].vbase(), s->f[BMQ_F_VFWD_Z].vbase()},
+        {s->f[BMQ_F_SFWD_X].vbase(), s->f[BMQ_F_SFWD_Y].vbase(), s->f[BMQ_F_SFWD_Z].vbase()}};
+    BMQ_CK(launch_forward(s->stream, s->g, own(s, 0), s->f[BMQ_F_U].vbase(), s->f[BMQ_F_V].vbase(),
+                          s->f[BMQ_F_W].vbase(), 2, maps, s->cfldt, dt));
+    return BMQ_OK;
+}
+
+// BimocqSolver::semilagAdvect (BimocqSolver.cpp:645-668): traces back with -dt
+int stage_semilag(bmq3d_solver *s, float dt)
+{
+    int st = ensure_semi(s);
+    if (st != BMQ_OK) return st;
+    const float *u = s->f[BMQ_F_U].vbase(), *v = s->f[BMQ_F_V].vbase(), *w = s->f[BMQ_F_W].vbase();
+    for (int c = 0; c < 3; ++c) {
+        float *o = s->f[BMQ_F_U_SEMI + c].vbase();
+        const float *src = s->f[BMQ_F_U + c].vbase();
+        Stag sg = stag_of(BMQ_F_U + c);
+        BMQ_CK(launch_semilag(s->stream, s->g, own(s, sg.dz), sg, u, v, w, 1, &o, &src, s->cfldt, -dt));
+    }
+    float *o2[2] = {s->f[BMQ_F_RHO_SEMI].vbase(), s->f[BMQ_F_T_SEMI].vbase()};
+    const float *s2[2] = {s->f[BMQ_F_RHO].vbase(), s->f[BMQ_F_T].vbase()};
+    BMQ_CK(launch_semilag(s->stream, s->g, own(s, 0), Stag{0, 0, 0}, u, v, w, 2, o2, s2, s->cfldt, -dt));
+    return BMQ_OK;
+}
+
+void map_ptrs(bmq3d_solver *s, int first, const float *out[3])
+{
+    for (int c = 0; c < 3; ++c) out[c] = s->f[first + c].vbase();
+}
+
+// which: 0 velocity (three staggered components, one launch each), 1 scalars (rho+T in one launch)
+int stage_advect(bmq3d_solver *s, int which)
+{
+    const float *chi[3];
+    if (which == 0) {
+        map_ptrs(s, BMQ_F_VBWD_X, chi);
+        for (int c = 0; c < 3; ++c) {
+            float *o = s->scratch[c].vbase();
+            const float *init = s->f[BMQ_F_U_INIT + c].vbase();
+            Stag sg = stag_of(BMQ_F_U + c);
+            BMQ_CK(launch_advect(s->stream, s->g, own(s, sg.dz), sg, false, 1, &o, &init, chi));
+        }
+    } else {
+        map_ptrs(s, BMQ_F_SBWD_X, chi);
+        float *o[2] = {s->scratch[3].vbase(), s->scratch[4].vbase()};
+        const float *init[2] = {s->f[BMQ_F_RHO_INIT].vbase(), s->f[BMQ_F_T_INIT].vbase()};
+        BMQ_CK(launch_advect(s->stream, s->g, own(s, 0), Stag{0, 0, 0}, false, 2, o, init, chi));
+    }
+    return BMQ_OK;
+}
+
+int stage_error(bmq3d_solver *s, int which)
+{
+    const float *psi[3];
+    if (which == 0) {
+        map_ptrs(s, BMQ_F_VFWD_X, psi);
+        for (int c = 0; c < 3; ++c) {
+            float *e = s->scratch[5 + c].vbase();
+            const float *src = s->scratch[c].vbase();
+            const float *init = s->f[BMQ_F_U_INIT + c].vbase();
+            Stag sg = stag_of(BMQ_F_U + c);
+            BMQ_CK(launch_error(s->stream, s->g, own(s, sg.dz), sg, false, 1, &e, &src, &init, psi));
+        }
+    } else {
+        map_ptrs(s, BMQ_F_SFWD_X, psi);
+        float *e[2] = {s->scratch[8].vbase(), s->scratch[9].vbase()};
+        const float *src[2] = {s->scratch[3].vbase(), s->scratch[4].vbase()};
+        const float *init[2] = {s->f[BMQ_F_RHO_INIT].vbase(), s->f[BMQ_F_T_INIT].vbase()};
+        BMQ_CK(launch_error(s->stream, s->g, own(s, 0), Stag{0, 0, 0}, false, 2, e, src, init, psi));
+    }
+    return BMQ_OK;
+}
+
+int stage_apply(bmq3d_solver *s, int which)
+{
+    const float *chi[3];
+    if (which == 0) {
+        map_ptrs(s, BMQ_F_VBWD_X, chi);
+        for (int c = 0; c < 3; ++c) {
+            float *o = s->f[BMQ_F_U + c].vbase();
+            const float *adv = s->scratch[c].vbase();
+            const float *e = s->scratch[5 + c].vbase();
+            Stag sg = stag_of(BMQ_F_U + c);
+            BMQ_CK(launch_apply_clamp(s->stream, s->g, own(s, sg.dz), sg, false, 1, &o, &adv, &e, chi));
+        }
+    } else {
+        map_ptrs(s, BMQ_F_SBWD_X, chi);
+        float *o[2] = {s->f[BMQ_F_RHO].vbase(), s->f[BMQ_F_T].vbase()};
+        const float *adv[2] = {s->scratch[3].vbase(), s->scratch[4].vbase()};
+        const float *e[2] = {s->scratch[8].vbase(), s->scratch[9].vbase()};
+        BMQ_CK(launch_apply_clamp(s->stream, s->g, own(s, 0), Stag{0, 0, 0}, false, 2, o, adv, e, chi));
+    }
+    return BMQ_OK;
+}
+
+// Two-level blend (Mapping.cpp:196-201, 228-233).  The reference launches doubleAdvect_kernel
+// even with blend 1, where it computes f*1 + 0*p = f; that launch is skipped here.
+int stage_blend(bmq3d_solver *s, int which)
+{
+    const int count = which == 0 ? s->vel_reinit_count : s->scalar_reinit_count;
+    if (count == 0 || s->blend == 1.0f) return BMQ_OK;
+    const float *chi[3], *chip[3];
+    if (which == 0) {
+        map_ptrs(s, BMQ_F_VBWD_X, chi);
+        map_ptrs(s, BMQ_F_VBWDP_X, chip);
+        for (int c = 0; c < 3; ++c) {
+            float *fl = s->f[BMQ_F_U + c].vbase();
+            const float *pv = s->f[BMQ_F_U_PREV + c].vbase();
+            Stag sg = stag_of(BMQ_F_U + c);
+            BMQ_CK(launch_double_advect(s->stream, s->g, own(s, sg.dz), sg, false, 1, &fl, &pv, chi, chip, s->blend));
+        }
+    } else {
+        map_ptrs(s, BMQ_F_SBWD_X, chi);
+        map_ptrs(s, BMQ_F_SBWDP_X, chip);
+        float *fl[2] = {s->f[BMQ_F_RHO].vbase(), s->f[BMQ_F_T].vbase()};
+        const float *pv[2] = {s->f[BMQ_F_RHO_PREV].vbase(), s->f[BMQ_F_T_PREV].vbase()};
+        BMQ_CK(launch_double_advect(s->stream, s->g, own(s, 0), Stag{0, 0, 0}, false, 2, fl, pv, chi, chip, s->blend));
+    }
+    return BMQ_OK;
+}
+
+// estimateDistortion for both mappers (Mapping.cpp:91-118) with the max on the device
+int stage_distortion(bmq3d_solver *s, float *vel_d2, float *sca_d2, float *dispz)
+{
+    BMQ_CK(cudaMemsetAsync(s->d_red, 0, 4 * sizeof(float), s->stream));
+    const float *const b[2][3] = {
+        {s->f[BMQ_F_VBWD_X].vbase(), s->f[BMQ_F_VBWD_Y].vbase(), s->f[BMQ_F_VBWD_Z].vbase()},
+        {s->f[BMQ_F_SBWD_X].vbase(), s->f[BMQ_F_SBWD_Y].vbase(), s->f[BMQ_F_SBWD_Z].vbase()}};
+    const float *const f[2][3] = {
+        {s->f[BMQ_F_VFWD_X].vbase(), s->f[BMQ_F_VFWD_Y].vbase(), s->f[BMQ_F_VFWD_Z].vbase()},
+        {s->f[BMQ_F_SFWD_X].vbase(), s->f[BMQ_F_SFWD_Y].vbase(), s->f[BMQ_F_SFWD_Z].vbase()}};
+    float *d2[2] = {s->d_red + 1, s->d_red + 2};
+    BMQ_CK(launch_estimate(s->stream, s->g, own(s, 0), 2, b, f, nullptr, d2, s->d_red + 3, nullptr));
+    BMQ_CK(cudaMemcpyAsync(s->h_red, s->d_red, 4 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    *vel_d2 = s->h_red[1];
+    *sca_d2 = s->h_red[2];
+    *dispz = s->h_red[3] / s->h;
+    return BMQ_OK;
+}
+
+// reinit decision, BimocqSolver.cpp:165-185
+void decide(bmq3d_solver *s, int framenum, float dt, float vel_d2, float sca_d2)
+{
+    s->proj_coeff = 2.f;
+    s->vel_reinit = s->scalar_reinit = false;
+    const float vd = sqrtf(vel_d2) / (s->max_v * dt);
+    const float sd = sqrtf(sca_d2) / (s->max_v * dt);
+    s->stats.vel_distortion = vd;
+    s->stats.scalar_distortion = sd;
+    if (vd > 1.f || framenum - s->vel_last_reinit > 10) {
+        s->vel_reinit = true;
+        s->vel_last_reinit = framenum;
+        s->proj_coeff = 1.f;
+    }
+    if (sd > 5.f || framenum - s->scalar_last_reinit > 30) {
+        s->scalar_reinit = true;
+        s->scalar_last_reinit = framenum;
+    }
+    s->stats.vel_reinit = s->vel_reinit;
+    s->stats.scalar_reinit = s->scalar_reinit;
+}
+
+// accumulate: init += 1*quad9[d_ext o psi] then += proj_coeff*quad9[d_proj o psi]  (BimocqSolver.cpp:193-196)
+int stage_accumulate(bmq3d_solver *s, int which)
+{
+    const float *psi[3];
+    if (which == 0) {
+        map_ptrs(s, BMQ_F_VFWD_X, psi);
+        const float coeff[2] = {1.f, s->proj_coeff};
+        for (int c = 0; c < 3; ++c) {
+            float *t = s->f[BMQ_F_U_INIT + c].vbase();
+            const float *ch[2] = {s->f[BMQ_F_DU_EXT + c].vbase(), s->f[BMQ_F_DU_PROJ + c].vbase()};
+            Stag sg = stag_of(BMQ_F_U + c);
+            BMQ_CK(launch_cumulate(s->stream, s->g, own(s, sg.dz), sg, false, 1, 2, &t, ch, coeff, psi));
+        }
+    } else {
+        map_ptrs(s, BMQ_F_SFWD_X, psi);
+        const float one = 1.f;
+        float *t[2] = {s->f[BMQ_F_RHO_INIT].vbase(), s->f[BMQ_F_T_INIT].vbase()};
+        const float *ch[2] = {s->f[BMQ_F_DRHO_EXT].vbase(), s->f[BMQ_F_DT_EXT].vbase()};
+        BMQ_CK(launch_cumulate(s->stream, s->g, own(s, 0), Stag{0, 0, 0}, false, 2, 1, t, ch, &one, psi));
+    }
+    return BMQ_OK;
+}
+
+// phase 0: reinitializeMapping + velocityReinitialize/scalarReinitialize by rotation
+// phase 1 (velocity only): the extra accumulate(duproj, 1.0) of BimocqSolver.cpp:214
+int stage_reinit(bmq3d_solver *s, int which, int phase)
+{
+    if (which == 0) {
+        if (phase == 0) {
+            s->vel_reinit_count++;
+            for (int c = 0; c < 3; ++c) {
+                std::swap(s->f[BMQ_F_VBWDP_X + c], s->f[BMQ_F_VBWD_X + c]);   // chi_prev <- chi
+                std::swap(s->f[BMQ_F_U_PREV + c], s->f[BMQ_F_U_INIT + c]);    // prev <- init
+            }
+            int st = identity_fill(s, BMQ_F_VBWD_X);
+            if (st == BMQ_OK) st = identity_fill(s, BMQ_F_VFWD_X);
+            for (int c = 0; c < 3 && st == BMQ_OK; ++c) st = copy_field(s, s->f[BMQ_F_U_INIT + c], s->f[BMQ_F_U + c]);
+            return st;
+        }
+        const float *psi[3];
+        map_ptrs(s, BMQ_F_VFWD_X, psi);
+        const float one = 1.f;
+        for (int c = 0; c < 3; ++c) {
+            float *t = s->f[BMQ_F_U_INIT + c].vbase();
+            const float *ch = s->f[BMQ_F_DU_PROJ + c].vbase();
+            Stag sg = stag_of(BMQ_F_U + c);
+            BMQ_CK(launch_cumulate(s->stream, s->g, own(s, sg.dz), sg, false, 1, 1, &t, &ch, &one, psi));
+        }
+        return BMQ_OK;
+    }
+    if (phase != 0) return BMQ_OK;
+    s->scalar_reinit_count++;
+    for (int c = 0; c < 3; ++c) std::swap(s->f[BMQ_F_SBWDP_X + c], s->f[BMQ_F_SBWD_X + c]);
+    std::swap(s->f[BMQ_F_RHO_PREV], s->f[BMQ_F_RHO_INIT]);
+    std::swap(s->f[BMQ_F_T_PREV], s->f[BMQ_F_T_INIT]);
+    int st = identity_fill(s, BMQ_F_SBWD_X);
+    if (st == BMQ_OK) st = identity_fill(s, BMQ_F_SFWD_X);
+    if (st == BMQ_OK) st = copy_field(s, s->f[BMQ_F_RHO_INIT], s->f[BMQ_F_RHO]);
+    if (st == BMQ_OK) st = copy_field(s, s->f[BMQ_F_T_INIT], s->f[BMQ_F_T]);
+    return st;
+}
+
+#define RET_IF(x) do { int _s = (x); if (_s != BMQ_OK) return _s; } while (0)
+#define NEED(s) do { if (!(s)) return set_error(BMQ_ERR_ARG, "%s: null solver handle", __func__); } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int bmq3d_create_slab(int ni, int nj, int nk, float h, float blend_coeff, int k_own0, int k_own1, int halo,
+                      bmq3d_solver **out)
+{
+    if (!out) return set_error(BMQ_ERR_ARG, "bmq3d_create: out is null");
+    *out = nullptr;
+    if (!require_device()) return BMQ_ERR_NODEVICE;
+    if (ni < 8 || nj < 8 || nk < 8 || !(h > 0.f) || k_own0 < 0 || k_own1 > nk || k_own0 >= k_own1 || halo < 0)
+        return set_error(BMQ_ERR_ARG, "bmq3d_create: bad grid %dx%dx%d h=%g slab [%d,%d) halo %d", ni, nj, nk,
+                         (double)h, k_own0, k_own1, halo);
+    if ((long long)(ni + 1) * (nj + 1) * (long long)(nk + 2) >= (1ll << 31))
+        return set_error(BMQ_ERR_ARG, "bmq3d_create: grid too large for 32-bit indexing");
+    bmq3d_solver *s = new (std::nothrow) bmq3d_solver();
+    if (!s) return set_error(BMQ_ERR_ARG, "bmq3d_create: out of host memory");
+    s->ni = ni; s->nj = nj; s->nk = nk; s->h = h; s->blend = blend_coeff;
+    s->k0 = k_own0; s->k1 = k_own1; s->halo = halo;
+    s->g = make_grid(ni, nj, nk, h);
+    memset(&s->stats, 0, sizeof s->stats);
+    int st = BMQ_OK;
+    for (int id = 0; id < BMQ_F_U_SEMI && st == BMQ_OK; ++id) st = alloc_field(s, s->f[id], stag_of(id));
+    for (int q = 0; q < N_SCRATCH && st == BMQ_OK; ++q) st = alloc_field(s, s->scratch[q], stag_of(SCRATCH_BASE + q));
+    for (int q = 0; q < N_TMPMAP && st == BMQ_OK; ++q) st = alloc_field(s, s->tmpmap[q], Stag{0, 0, 0});
+    if (st == BMQ_OK) st = check_cuda(cudaMalloc(&s->d_red, 8 * sizeof(float)), "cudaMalloc", __FILE__, __LINE__);
+    if (st == BMQ_OK) st = check_cuda(cudaMallocHost(&s->h_red, 8 * sizeof(float)), "cudaMallocHost", __FILE__, __LINE__);
+    if (st == BMQ_OK) st = bmq3d_reset(s);
+    if (st != BMQ_OK) { bmq3d_destroy(s); return st; }
+    *out = s;
+    return BMQ_OK;
+}
+
+int bmq3d_create(int ni, int nj, int nk, float h, float blend_coeff, bmq3d_solver **out)
+{
+    return bmq3d_create_slab(ni, nj, nk, h, blend_coeff, 0, nk, 0, out);
+}
+
+int bmq3d_destroy(bmq3d_solver *s)
+{
+    if (!s) return BMQ_OK;
+    for (auto &fd : s->f) if (fd.alloc) cudaFree(fd.alloc);
+    for (auto &fd : s->scratch) if (fd.alloc) cudaFree(fd.alloc);
+    for (auto &fd : s->tmpmap) if (fd.alloc) cudaFree(fd.alloc);
+    if (s->d_red) cudaFree(s->d_red);
+    if (s->h_red) cudaFreeHost(s->h_red);
+    delete s;
+    return BMQ_OK;
+}
+
+int bmq3d_set_stream(bmq3d_solver *s, void *stream)
+{
+    NEED(s);
+    s->stream = (cudaStream_t)stream;
+    return BMQ_OK;
+}
+
+int bmq3d_field_ptr(bmq3d_solver *s, int field_id, float **dev_ptr, int *first_plane, int *n_planes, int *nx,
+                    int *ny)
+{
+    NEED(s);
+    if (field_id >= BMQ_F_U_SEMI && field_id <= BMQ_F_T_SEMI) RET_IF(ensure_semi(s));
+    Field *fd = field_of(s, field_id);
+    if (!fd || !fd->alloc) return set_error(BMQ_ERR_ARG, "bmq3d_field_ptr: bad field id %d", field_id);
+    if (dev_ptr) *dev_ptr = fd->alloc;
+    if (first_plane) *first_plane = fd->p0;
+    if (n_planes) *n_planes = fd->p1 - fd->p0;
+    if (nx) *nx = fd->nx;
+    if (ny) *ny = fd->ny;
+    return BMQ_OK;
+}
+
+int bmq3d_upload(bmq3d_solver *s, int field_id, const float *host)
+{
+    NEED(s);
+    if (field_id >= BMQ_F_U_SEMI && field_id <= BMQ_F_T_SEMI) RET_IF(ensure_semi(s));
+    Field *fd = field_of(s, field_id);
+    if (!fd || !fd->alloc || !host) return set_error(BMQ_ERR_ARG, "bmq3d_upload: bad field id %d or null host", field_id);
+    BMQ_CK(cudaMemcpyAsync(fd->alloc, host, fd->stored_elems() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    return BMQ_OK;
+}
+
+int bmq3d_download(bmq3d_solver *s, int field_id, float *host)
+{
+    NEED(s);
+    if (field_id >= BMQ_F_U_SEMI && field_id <= BMQ_F_T_SEMI) RET_IF(ensure_semi(s));
+    Field *fd = field_of(s, field_id);
+    if (!fd || !fd->alloc || !host) return set_error(BMQ_ERR_ARG, "bmq3d_download: bad field id %d or null host", field_id);
+    BMQ_CK(cudaMemcpyAsync(host, fd->alloc, fd->stored_elems() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    return BMQ_OK;
+}
+
+int bmq3d_reset(bmq3d_solver *s)
+{
+    NEED(s);
+    const int maps[6] = {BMQ_F_VFWD_X, BMQ_F_VBWD_X, BMQ_F_VBWDP_X, BMQ_F_SFWD_X, BMQ_F_SBWD_X, BMQ_F_SBWDP_X};
+    for (int m : maps) RET_IF(identity_fill(s, m));
+    RET_IF(identity_fill_tmp(s, 0));
+    RET_IF(identity_fill_tmp(s, 3));
+    for (int c = 0; c < 5; ++c) {
+        RET_IF(copy_field(s, s->f[BMQ_F_U_INIT + c], s->f[BMQ_F_U + c]));
+        RET_IF(copy_field(s, s->f[BMQ_F_U_PREV + c], s->f[BMQ_F_U + c]));
+    }
+    s->vel_last_reinit = s->scalar_last_reinit = 0;
+    s->vel_reinit_count = s->scalar_reinit_count = 0;
+    s->proj_coeff = 2.f;
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    return BMQ_OK;
+}
+
+int bmq3d_stage_maxvel(bmq3d_solver *s, float *max_abs_out)
+{
+    NEED(s);
+    float m = 0.f;
+    RET_IF(stage_maxvel(s, &m));
+    if (max_abs_out) *max_abs_out = m;
+    return BMQ_OK;
+}
+int bmq3d_stage_set_cfl(bmq3d_solver *s, int framenum, float global_max_abs) { NEED(s); set_cfl(s, framenum, global_max_abs); return BMQ_OK; }
+int bmq3d_stage_dmc_substep(bmq3d_solver *s, float substep) { NEED(s); return stage_dmc(s, substep); }
+int bmq3d_stage_forward(bmq3d_solver *s, float dt) { NEED(s); return stage_forward(s, dt); }
+int bmq3d_stage_semilag(bmq3d_solver *s, float dt) { NEED(s); return stage_semilag(s, dt); }
+static int for_which(bmq3d_solver *s, int which, int (*fn)(bmq3d_solver *, int))
+{
+    if (which < 0 || which > 2) return set_error(BMQ_ERR_ARG, "which must be 0 (velocity), 1 (scalars) or 2 (both)");
+    if (which != 1) RET_IF(fn(s, 0));
+    if (which != 0) RET_IF(fn(s, 1));
+    return BMQ_OK;
+}
+int bmq3d_stage_advect(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_advect); }
+int bmq3d_stage_error(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_error); }
+int bmq3d_stage_apply(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_apply); }
+int bmq3d_stage_blend(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_blend); }
+int bmq3d_stage_accumulate(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_accumulate); }
+int bmq3d_stage_distortion(bmq3d_solver *s, float *vel_d2, float *scalar_d2, float *max_disp_z)
+{
+    NEED(s);
+    float a = 0, b = 0, c = 0;
+    RET_IF(stage_distortion(s, &a, &b, &c));
+    if (vel_d2) *vel_d2 = a;
+    if (scalar_d2) *scalar_d2 = b;
+    if (max_disp_z) *max_disp_z = c;
+    s->stats.max_disp_z = c;
+    return BMQ_OK;
+}
+int bmq3d_stage_decide(bmq3d_solver *s, int framenum, float dt, float vel_d2, float scalar_d2)
+{
+    NEED(s);
+    decide(s, framenum, dt, vel_d2, scalar_d2);
+    return BMQ_OK;
+}
+int bmq3d_stage_reinit(bmq3d_solver *s, int which, int phase)
+{
+    NEED(s);
+    if (which != 0 && which != 1) return set_error(BMQ_ERR_ARG, "bmq3d_stage_reinit: which must be 0 or 1");
+    int st = stage_reinit(s, which, phase);
+    s->stats.vel_reinit_count = s->vel_reinit_count;
+    s->stats.scalar_reinit_count = s->scalar_reinit_count;
+    return st;
+}
+
+// Phase A, BimocqSolver.cpp:90-126
+int bmq3d_advect(bmq3d_solver *s, int framenum, float dt, int with_semilag)
+{
+    NEED(s);
+    if (!(dt > 0.f)) return set_error(BMQ_ERR_ARG, "bmq3d_advect: dt must be positive");
+    float mabs = 0.f;
+    RET_IF(stage_maxvel(s, &mabs));
+    set_cfl(s, framenum, mabs);
+    // updateBackward, Mapping.cpp:7-24 / 354-368: the float loop that fixes the sub-step sequence
+    float T = 0.f, substep = s->cfldt;
+    int n = 0;
+    while (T < dt) {
+        if (T + substep > dt) substep = dt - T;
+        RET_IF(stage_dmc(s, substep));
+        T += substep;
+        if (++n > 4096) return set_error(BMQ_ERR_ARG, "bmq3d_advect: more than 4096 CFL sub-steps (dt/cfldt too large)");
+    }
+    s->stats.n_substeps = n;
+    RET_IF(stage_forward(s, dt));
+    if (with_semilag) RET_IF(stage_semilag(s, dt));
+    for (int which = 0; which < 2; ++which) {
+        RET_IF(stage_advect(s, which));
+        RET_IF(stage_error(s, which));
+        RET_IF(stage_apply(s, which));
+        RET_IF(stage_blend(s, which));
+    }
+    return BMQ_OK;
+}
+
+// Phase B, BimocqSolver.cpp:164-229
+int bmq3d_accumulate(bmq3d_solver *s, int framenum, float dt)
+{
+    NEED(s);
+    float vd2 = 0, sd2 = 0, dz = 0;
+    RET_IF(stage_distortion(s, &vd2, &sd2, &dz));
+    s->stats.max_disp_z = dz;
+    decide(s, framenum, dt, vd2, sd2);
+    RET_IF(stage_accumulate(s, 0));
+    RET_IF(stage_accumulate(s, 1));
+    if (s->vel_reinit) {
+        RET_IF(stage_reinit(s, 0, 0));
+        RET_IF(stage_reinit(s, 0, 1));
+    }
+    if (s->scalar_reinit) RET_IF(stage_reinit(s, 1, 0));
+    s->stats.vel_reinit_count = s->vel_reinit_count;
+    s->stats.scalar_reinit_count = s->scalar_reinit_count;
+    return BMQ_OK;
+}
+
+int bmq3d_get_stats(bmq3d_solver *s, bmq3d_stats *out)
+{
+    NEED(s);
+    if (!out) return set_error(BMQ_ERR_ARG, "bmq3d_get_stats: out is null");
+    *out = s->stats;
+    return BMQ_OK;
+}
+
+int bmq3d_advect_host(bmq3d_solver *s, int framenum, float dt, float *u, float *v, float *w, float *rho, float *T)
+{
+    NEED(s);
+    float *host[5] = {u, v, w, rho, T};
+    for (int c = 0; c < 5; ++c) {
+        if (!host[c]) return set_error(BMQ_ERR_ARG, "bmq3d_advect_host: null field pointer %d", c);
+        Field &fd = s->f[BMQ_F_U + c];
+        BMQ_CK(cudaMemcpyAsync(fd.alloc, host[c], fd.stored_elems() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    }
+    RET_IF(bmq3d_advect(s, framenum, dt, 0));
+    for (int c = 0; c < 5; ++c) {
+        Field &fd = s->f[BMQ_F_U + c];
+        BMQ_CK(cudaMemcpyAsync(host[c], fd.alloc, fd.stored_elems() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    return BMQ_OK;
+}
+
+int bmq3d_accumulate_host(bmq3d_solver *s, int framenum, float dt, const float *u_forced, const float *v_forced,
+                          const float *w_forced, const float *u_final, const float *v_final, const float *w_final,
+                          const float *rho_final, const float *T_final)
+{
+    NEED(s);
+    const float *forced[3] = {u_forced, v_forced, w_forced};
+    const float *fin[5] = {u_final, v_final, w_final, rho_final, T_final};
+    for (int c = 0; c < 5; ++c)
+        if (!fin[c] || (c < 3 && !forced[c])) return set_error(BMQ_ERR_ARG, "bmq3d_accumulate_host: null field %d", c);
+    // The change fields are formed on the device exactly as the reference forms them on the host
+    // (BimocqSolver.cpp:149-162): d_ext = forced - advected, d_proj = final - forced,
+    // d_scalar = final - advected; the device copy of the current fields becomes `final`.
+    for (int c = 0; c < 3; ++c) {
+        Field &cur = s->f[BMQ_F_U + c], &ext = s->f[BMQ_F_DU_EXT + c], &proj = s->f[BMQ_F_DU_PROJ + c];
+        const size_t n = cur.stored_elems();
+        BMQ_CK(cudaMemcpyAsync(proj.alloc, forced[c], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        BMQ_CK(launch_add_field(s->stream, ext.alloc, proj.alloc, cur.alloc, -1.f, n));     // forced - advected
+        BMQ_CK(cudaMemcpyAsync(cur.alloc, fin[c], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        BMQ_CK(launch_add_field(s->stream, proj.alloc, cur.alloc, proj.alloc, -1.f, n));    // final - forced
+    }
+    for (int c = 0; c < 2; ++c) {
+        Field &cur = s->f[BMQ_F_RHO + c], &ext = s->f[BMQ_F_DRHO_EXT + c], &tmp = s->scratch[3 + c];
+        const size_t n = cur.stored_elems();
+        BMQ_CK(cudaMemcpyAsync(tmp.alloc, fin[3 + c], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        BMQ_CK(launch_add_field(s->stream, ext.alloc, tmp.alloc, cur.alloc, -1.f, n));      // final - advected
+        BMQ_CK(cudaMemcpyAsync(cur.alloc, tmp.alloc, n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        // the advect scratch must keep its zero ring (see file header): restore it by clearing
+        BMQ_CK(cudaMemsetAsync(tmp.alloc, 0, n * sizeof(float), s->stream));
+    }
+    RET_IF(bmq3d_accumulate(s, framenum, dt));
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    return BMQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+/*
+ * bimocq_b200.h -- C ABI of libbimocq_b200.so: the BiMocq^2 advection hot path for NVIDIA B200
+ * (sm_100a).  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Two groups of entry points:
+ *
+ *  1. LEGACY DROP-IN SYMBOLS.  The 14 hot-path `extern "C" void gpu_*` functions of the
+ *     reference, with byte-identical prototypes, so that the reference's gpuMapper /
+ *     MapperBase / MapperBaseGPU (bimocq3D/GPU_Advection.h:110-627, bimocq3D/Mapping.cpp) link
+ *     against this library unchanged.  Each prototype cites the reference declaration it
+ *     replaces.  All pointers are DEVICE pointers to dense x-fastest float arrays
+ *     (idx = i + nx*j + nx*ny*k) of the sizes the reference uses; they run on the legacy
+ *     default stream, return void, and latch errors for bmq_last_error().
+ *
+ *  2. HANDLE API (bmq3d_*).  Device-resident solver state with the fused kernels and the
+ *     reinitialisation scheduler of BimocqSolver::advanceBimocq (bimocq3D/BimocqSolver.cpp:88-230)
+ *     inside.  Returns int status codes (0 = BMQ_OK), never exits the process.
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device and fails loudly without one.
+ */
+#ifndef BIMOCQ_B200_H
+#define BIMOCQ_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status / errors */
+enum {
+    BMQ_OK = 0,
+    BMQ_ERR_CUDA = 1,       /* a CUDA runtime call or kernel launch failed */
+    BMQ_ERR_ARG = 2,        /* bad argument (null handle, bad field id, bad size) */
+    BMQ_ERR_HALO = 3,       /* z-slab halo narrower than the measured map displacement */
+    BMQ_ERR_NODEVICE = 4    /* no CUDA device visible */
+};
+/* Last error message recorded on the calling thread's process (empty string if none). */
+const char *bmq_last_error(void);
+/* Clears the latched error; returns the status code that was latched. */
+int bmq_clear_error(void);
+/* Library version string, e.g. "bimocq_b200 0.1 (sm_100a)". */
+const char *bmq_version(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+unsigned long long bmq_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ legacy drop-in symbols */
+/* replaces GPU_Advection.h:26-28 (def. GPU_kernel.cu:567-574): psi <- trace(psi, +dt), in place */
+void gpu_solve_forward(float *u, float *v, float *w, float *x_fwd, float *y_fwd, float *z_fwd,
+                       float h, int ni, int nj, int nk, float cfldt, float dt);
+/* replaces GPU_Advection.h:30-33 (def. GPU_kernel.cu:576-584): one DMC sub-step, in -> out */
+void gpu_solve_backwardDMC(float *u, float *v, float *w, float *x_in, float *y_in, float *z_in,
+                           float *x_out, float *y_out, float *z_out, float h, int ni, int nj,
+                           int nk, float substep);
+/* replaces GPU_Advection.h:35-38 (def. GPU_kernel.cu:586-598) */
+void gpu_advect_velocity(float *u, float *v, float *w, float *u_init, float *v_init,
+                         float *w_init, float *backward_x, float *backward_y, float *backward_z,
+                         float h, int ni, int nj, int nk, bool is_point);
+/* replaces GPU_Advection.h:40-44 (def. GPU_kernel.cu:600-618) */
+void gpu_advect_vel_double(float *u, float *v, float *w, float *utemp, float *vtemp, float *wtemp,
+                           float *backward_x, float *backward_y, float *backward_z,
+                           float *backward_xprev, float *backward_yprev, float *backward_zprev,
+                           float h, int ni, int nj, int nk, bool is_point, float blend_coeff);
+/* replaces GPU_Advection.h:46-48 (def. GPU_kernel.cu:620-627) */
+void gpu_advect_field(float *field, float *field_init, float *backward_x, float *backward_y,
+                      float *backward_z, float h, int ni, int nj, int nk, bool is_point);
+/* replaces GPU_Advection.h:50-53 (def. GPU_kernel.cu:629-638) */
+void gpu_advect_field_double(float *field, float *field_init, float *backward_x,
+                             float *backward_y, float *backward_z, float *backward_xprev,
+                             float *backward_yprev, float *backward_zprev, float h, int ni, int nj,
+                             int nk, bool is_point, float blend_coeff);
+/* replaces GPU_Advection.h:55-58 (def. GPU_kernel.cu:684-696) */
+void gpu_accumulate_velocity(float *u_change, float *v_change, float *w_change, float *du_init,
+                             float *dv_init, float *dw_init, float *forward_x, float *forward_y,
+                             float *forward_z, float h, int ni, int nj, int nk, bool is_point,
+                             float coeff);
+/* replaces GPU_Advection.h:60-62 (def. GPU_kernel.cu:698-705) */
+void gpu_accumulate_field(float *field_change, float *dfield_init, float *forward_x,
+                          float *forward_y, float *forward_z, float h, int ni, int nj, int nk,
+                          bool is_point, float coeff);
+/* replaces GPU_Advection.h:64-67 (def. GPU_kernel.cu:707-716): per-cell squared distortion -> du */
+void gpu_estimate_distortion(float *du, float *x_init, float *y_init, float *z_init, float *x_fwd,
+                             float *y_fwd, float *z_fwd, float h, int ni, int nj, int nk);
+/* replaces GPU_Advection.h:69 (def. GPU_kernel.cu:729-734): field1 += coeff*field2 */
+void gpu_add(float *field1, float *field2, float coeff, int number);
+/* replaces GPU_Advection.h:71-76 (def. GPU_kernel.cu:640-666).  Same aliasing contract as the
+ * reference: u_src receives the time-0 error, du/dv/dw are OVERWRITTEN with the pre-correction
+ * u/v/w, and u/v/w receive the compensated, extrema-clamped result. */
+void gpu_compensate_velocity(float *u, float *v, float *w, float *du, float *dv, float *dw,
+                             float *u_src, float *v_src, float *w_src, float *forward_x,
+                             float *forward_y, float *forward_z, float *backward_x,
+                             float *backward_y, float *backward_z, float h, int ni, int nj, int nk,
+                             bool is_point);
+/* replaces GPU_Advection.h:78-81 (def. GPU_kernel.cu:668-682) */
+void gpu_compensate_field(float *u, float *du, float *u_src, float *forward_x, float *forward_y,
+                          float *forward_z, float *backward_x, float *backward_y,
+                          float *backward_z, float h, int ni, int nj, int nk, bool is_point);
+/* replaces GPU_Advection.h:83-86 (def. GPU_kernel.cu:718-727) */
+void gpu_semilag(float *field, float *field_src, float *u, float *v, float *w, int dim_x,
+                 int dim_y, int dim_z, float h, int ni, int nj, int nk, float cfldt, float dt);
+/* replaces GPU_Advection.h:97 (def. GPU_kernel.cu:885-890): out = field1 + coeff*field2 */
+void gpu_add_field(float *out, float *field1, float *field2, float coeff, int number);
+
+/* ------------------------------------------------------------------ handle API (3D) */
+typedef struct bmq3d_solver bmq3d_solver;
+
+/* Field identifiers for bmq3d_field_ptr / bmq3d_upload / bmq3d_download.  Velocity faces are
+ * (ni+1)*nj*nk, ni*(nj+1)*nk, ni*nj*(nk+1); everything else ni*nj*nk.  Dense, x-fastest. */
+enum {
+    BMQ_F_U = 0, BMQ_F_V, BMQ_F_W, BMQ_F_RHO, BMQ_F_T,                 /* current fields          */
+    BMQ_F_U_INIT, BMQ_F_V_INIT, BMQ_F_W_INIT, BMQ_F_RHO_INIT, BMQ_F_T_INIT,
+    BMQ_F_U_PREV, BMQ_F_V_PREV, BMQ_F_W_PREV, BMQ_F_RHO_PREV, BMQ_F_T_PREV,
+    BMQ_F_DU_EXT, BMQ_F_DV_EXT, BMQ_F_DW_EXT, BMQ_F_DRHO_EXT, BMQ_F_DT_EXT, /* change: forces/sources */
+    BMQ_F_DU_PROJ, BMQ_F_DV_PROJ, BMQ_F_DW_PROJ,                       /* change: projection      */
+    BMQ_F_VFWD_X, BMQ_F_VFWD_Y, BMQ_F_VFWD_Z,                          /* velocity mapper psi     */
+    BMQ_F_VBWD_X, BMQ_F_VBWD_Y, BMQ_F_VBWD_Z,                          /* velocity mapper chi     */
+    BMQ_F_VBWDP_X, BMQ_F_VBWDP_Y, BMQ_F_VBWDP_Z,                       /* velocity mapper chi_prev*/
+    BMQ_F_SFWD_X, BMQ_F_SFWD_Y, BMQ_F_SFWD_Z,                          /* scalar mapper psi       */
+    BMQ_F_SBWD_X, BMQ_F_SBWD_Y, BMQ_F_SBWD_Z,
+    BMQ_F_SBWDP_X, BMQ_F_SBWDP_Y, BMQ_F_SBWDP_Z,
+    BMQ_F_U_SEMI, BMQ_F_V_SEMI, BMQ_F_W_SEMI, BMQ_F_RHO_SEMI, BMQ_F_T_SEMI, /* semi-Lagrangian fallback */
+    BMQ_F_COUNT
+};
+
+/* Per-step scalars the reference prints (BimocqSolver.cpp:95,170-173,215). */
+typedef struct bmq3d_stats {
+    float max_v;              /* getCFL(): max(1e-4, max|u|,|v|,|w|); h on frame 0 (BimocqSolver.cpp:94) */
+    float cfldt;              /* h / max|vel|                                                   */
+    int n_substeps;           /* DMC / RK3 sub-steps taken                                       */
+    float vel_distortion;     /* estimateDistortion / (max_v*dt), velocity mapper                */
+    float scalar_distortion;  /* same, scalar mapper                                             */
+    int vel_reinit;           /* 1 if the velocity maps were reinitialised this step             */
+    int scalar_reinit;
+    int vel_reinit_count;     /* MapperBase::total_reinit_count                                  */
+    int scalar_reinit_count;
+    float max_disp_z;         /* max |map_z - z| over both mappers, in cells (halo sizing)       */
+} bmq3d_stats;
+
+/* Creates a solver for an ni x nj x nk grid of cell size h on the current CUDA device.
+ * blend_coeff is MapperBase::blend_coeff (1 = one-level map, as every shipped scene uses).
+ * Slab form: the solver owns global planes [k_own0, k_own1) of a global grid of nk planes and
+ * stores planes [k_own0-halo, k_own1+halo) clipped to the domain.  k_own0=0,k_own1=nk,halo=0
+ * is the single-GPU case (bmq3d_create). */
+int bmq3d_create(int ni, int nj, int nk, float h, float blend_coeff, bmq3d_solver **out);
+int bmq3d_create_slab(int ni, int nj, int nk, float h, float blend_coeff, int k_own0, int k_own1,
+                      int halo, bmq3d_solver **out);
+int bmq3d_destroy(bmq3d_solver *s);
+/* Use `stream` (a cudaStream_t cast to void*) for all subsequent work; NULL = legacy default. */
+int bmq3d_set_stream(bmq3d_solver *s, void *stream);
+/* Device pointer of a field's first STORED plane and the global index of that plane. */
+int bmq3d_field_ptr(bmq3d_solver *s, int field_id, float **dev_ptr, int *first_plane,
+                    int *n_planes, int *nx, int *ny);
+/* Host <-> device copies of a whole stored field (pinned or pageable host memory). */
+int bmq3d_upload(bmq3d_solver *s, int field_id, const float *host);
+int bmq3d_download(bmq3d_solver *s, int field_id, float *host);
+/* BimocqSolver::velocityReinitialize / scalarReinitialize semantics for frame 0: init <- current,
+ * prev <- init, maps <- identity, counters <- 0.  Call after uploading the initial fields. */
+int bmq3d_reset(bmq3d_solver *s);
+
+/* Phase A of BimocqSolver::advanceBimocq (BimocqSolver.cpp:90-126): getCFL, update both map
+ * pairs, optional semi-Lagrangian fallback fields, advect + compensate (+ two-level blend)
+ * velocity, density and temperature.  Reads and overwrites U,V,W,RHO,T. */
+int bmq3d_advect(bmq3d_solver *s, int framenum, float dt, int with_semilag);
+/* Phase B (BimocqSolver.cpp:164-229): distortion estimate, reinit decision, accumulate the
+ * change fields D*_EXT (coeff 1) and D*_PROJ (coeff proj_coeff) into the init buffers,
+ * reinitialise when triggered.  The caller fills the change fields between the phases. */
+int bmq3d_accumulate(bmq3d_solver *s, int framenum, float dt);
+int bmq3d_get_stats(bmq3d_solver *s, bmq3d_stats *out);
+
+/* Whole step through HOST buffers (the reference's host-orchestrated solver keeps its fields on
+ * the host, Mapping.cpp:7-236).  bmq3d_advect_host uploads u,v,w,rho,T, runs phase A and
+ * downloads the advected fields into the same arrays.  The caller then applies its forces and
+ * its projection on the host and hands bmq3d_accumulate_host the velocity after the external
+ * forces (`*_forced`), the final velocity after projection and the final scalars; the change
+ * fields are formed on the device exactly as BimocqSolver.cpp:149-162 forms them
+ * (d_ext = forced - advected, d_proj = final - forced, d_scalar = final - advected) and phase B
+ * runs.  No pointer may be NULL; host arrays are dense, whole fields. */
+int bmq3d_advect_host(bmq3d_solver *s, int framenum, float dt, float *u, float *v, float *w,
+                      float *rho, float *T);
+int bmq3d_accumulate_host(bmq3d_solver *s, int framenum, float dt, const float *u_forced,
+                          const float *v_forced, const float *w_forced, const float *u_final,
+                          const float *v_final, const float *w_final, const float *rho_final,
+                          const float *T_final);
+
+/* ---- fine-grained stages for the z-slab driver (one call = one kernel over owned planes).
+ * The multi-GPU driver exchanges halos between these calls.  `which` = 0 velocity mapper,
+ * 1 scalar mapper, 2 both. */
+int bmq3d_stage_maxvel(bmq3d_solver *s, float *max_abs_out);          /* local max|u|,|v|,|w| */
+int bmq3d_stage_set_cfl(bmq3d_solver *s, int framenum, float global_max_abs);
+int bmq3d_stage_dmc_substep(bmq3d_solver *s, float substep);          /* both mappers, ping-pong */
+int bmq3d_stage_forward(bmq3d_solver *s, float dt);
+int bmq3d_stage_semilag(bmq3d_solver *s, float dt);
+int bmq3d_stage_advect(bmq3d_solver *s, int which);                   /* f_adv = quad9[init o chi] */
+int bmq3d_stage_error(bmq3d_solver *s, int which);                    /* e0 = quad9[f_adv o psi]-init */
+int bmq3d_stage_apply(bmq3d_solver *s, int which);                    /* f = clamp(f_adv-.5 quad9[e0 o chi]) */
+int bmq3d_stage_blend(bmq3d_solver *s, int which);                    /* two-level blend, if active */
+int bmq3d_stage_distortion(bmq3d_solver *s, float *vel_d2, float *scalar_d2, float *max_disp_z);
+int bmq3d_stage_decide(bmq3d_solver *s, int framenum, float dt, float vel_d2, float scalar_d2);
+int bmq3d_stage_accumulate(bmq3d_solver *s, int which);
+int bmq3d_stage_reinit(bmq3d_solver *s, int which, int phase);        /* phase 0: rotate+identity; 1: post-accumulate */
+/* Scratch fields the slab driver must also exchange (ids continue after BMQ_F_COUNT). */
+enum { BMQ_F_U_ADV = 64, BMQ_F_V_ADV, BMQ_F_W_ADV, BMQ_F_RHO_ADV, BMQ_F_T_ADV,
+       BMQ_F_U_ERR, BMQ_F_V_ERR, BMQ_F_W_ERR, BMQ_F_RHO_ERR, BMQ_F_T_ERR };
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIMOCQ_B200_H */

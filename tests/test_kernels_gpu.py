@@ -1,0 +1,190 @@
+"""GPU parity, kernel by kernel: every legacy extern "C" gpu_* symbol of libbimocq_b200.so against
+(a) the CPU oracle and (b) the reference's own CUDA kernels (oracle/_ref/libref3d.so, compiled
+unmodified from bimocq3D/GPU_kernel.cu) on identical seeded inputs.  Also pins the oracle against
+the reference kernels.  Grids are deliberately not multiples of the 32x8 thread tile; one case has
+a power-of-two h (exact-multiply fast path), one the reference scene's h = 0.2/ni (IEEE division).
+Tolerance: relative L-inf <= 1e-5 per call (helpers.TOL_STEP)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import TOL_STEP, Case3D, load_reference_lib, rel_linf, run_gpu_symbol
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"pow2": (40, 36, 44, 1.0 / 32), "general": (37, 41, 35, 0.2 / 37)}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, oracle):
+    ni, nj, nk, h = CASES[request.param]
+    return Case3D(ni, nj, nk, h, seed=7)
+
+
+@pytest.fixture(scope="module")
+def ours(cuda):
+    from gpufluidsimulation_b200 import load_library
+    lib = load_library()
+    return C.CDLL(lib._name)     # raw handle: helpers set the prototypes per call
+
+
+@pytest.fixture(scope="module")
+def ref(cuda):
+    lib = load_reference_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref3d.so not built")
+    return lib
+
+
+def _check(name, got, want, tol=TOL_STEP):
+    for idx, (g, w) in enumerate(zip(got, want)):
+        err = rel_linf(g, w)
+        assert np.isfinite(g).all(), f"{name}: output {idx} has non-finite values"
+        assert err <= tol, f"{name}: output {idx} rel Linf {err:.3e} > {tol:.1e}"
+
+
+def _three_way(name, args, oracle_fn, ours, ref, outputs):
+    """Run on the oracle, our library and the reference library; compare the arrays at `outputs`
+    (indices into the array-only list)."""
+    arrays = [a for a in args if isinstance(a, np.ndarray)]
+    from oracle import oracle3d as o3
+    o_arrays = [o3.padded_copy(a) for a in arrays]
+    oracle_fn(o_arrays)
+    mine = run_gpu_symbol(ours, name, args)
+    _check(name + " vs oracle", [mine[i] for i in outputs], [o_arrays[i] for i in outputs])
+    if ref is not None:
+        theirs = run_gpu_symbol(ref, name, args)
+        _check(name + " vs reference kernel", [mine[i] for i in outputs], [theirs[i] for i in outputs])
+        _check(name + ": oracle vs reference kernel", [o_arrays[i] for i in outputs], [theirs[i] for i in outputs])
+
+
+def test_solve_forward(case, oracle, ours, ref):
+    c = case
+    args = [c.u, c.v, c.w, *c.fwd, c.h, c.ni, c.nj, c.nk, c.cfldt, c.dt]
+    _three_way("gpu_solve_forward", args,
+               lambda a: oracle.gpu_solve_forward(*a, c.h, c.ni, c.nj, c.nk, c.cfldt, c.dt), ours, ref, [3, 4, 5])
+
+
+def test_solve_backward_dmc(case, oracle, ours, ref):
+    c = case
+    out = [np.zeros_like(m) for m in c.bwd]
+    args = [c.u, c.v, c.w, *c.bwd, *out, c.h, c.ni, c.nj, c.nk, 0.7 * c.cfldt]
+    _three_way("gpu_solve_backwardDMC", args,
+               lambda a: oracle.gpu_solve_backwardDMC(*a, c.h, c.ni, c.nj, c.nk, 0.7 * c.cfldt), ours, ref, [6, 7, 8])
+
+
+@pytest.mark.parametrize("kind", ["u", "w", "c"])
+def test_semilag(case, oracle, ours, ref, kind):
+    c = case
+    dx, dy, dz = oracle.DIMS[kind]
+    src = c.fields[kind]
+    args = [np.zeros_like(src), src, c.u, c.v, c.w, dx, dy, dz, c.h, c.ni, c.nj, c.nk, c.cfldt, -c.dt]
+    _three_way("gpu_semilag", args,
+               lambda a: oracle.gpu_semilag(*a, dx, dy, dz, c.h, c.ni, c.nj, c.nk, c.cfldt, -c.dt), ours, ref, [0])
+
+
+@pytest.mark.parametrize("is_point", [False, True])
+def test_advect_velocity(case, oracle, ours, ref, is_point):
+    c = case
+    f = c.fields
+    args = [np.zeros_like(f["u"]), np.zeros_like(f["v"]), np.zeros_like(f["w"]), f["u"], f["v"], f["w"], *c.bwd,
+            c.h, c.ni, c.nj, c.nk, is_point]
+
+    def run(a):
+        for q, kind in enumerate("uvw"):
+            oracle.advect(a[q], a[3 + q], a[6], a[7], a[8], c.h, c.ni, c.nj, c.nk, kind, is_point)
+
+    _three_way("gpu_advect_velocity", args, run, ours, ref, [0, 1, 2])
+
+
+def test_advect_field(case, oracle, ours, ref):
+    c = case
+    f = c.fields["c"]
+    args = [np.zeros_like(f), f, *c.bwd, c.h, c.ni, c.nj, c.nk, False]
+    _three_way("gpu_advect_field", args,
+               lambda a: oracle.advect(a[0], a[1], a[2], a[3], a[4], c.h, c.ni, c.nj, c.nk, "c"), ours, ref, [0])
+
+
+def test_compensate_velocity(case, oracle, ours, ref):
+    """All three outputs of the reference's contract: u (result), du (pre-correction copy), u_src (error)."""
+    c = case
+    f, g = c.fields, c.fields2
+    args = [f["u"], f["v"], f["w"], g["u"], g["v"], g["w"], np.zeros_like(f["u"]), np.zeros_like(f["v"]),
+            np.zeros_like(f["w"]), *c.fwd, *c.bwd, c.h, c.ni, c.nj, c.nk, False]
+
+    def run(a):
+        for q, kind in enumerate("uvw"):
+            oracle.gpu_compensate(a[q], a[3 + q], a[6 + q], a[9:12], a[12:15], c.h, c.ni, c.nj, c.nk, kind)
+
+    _three_way("gpu_compensate_velocity", args, run, ours, ref, list(range(9)))
+
+
+def test_compensate_field(case, oracle, ours, ref):
+    c = case
+    f, g = c.fields["c"], c.fields2["c"]
+    args = [f, g, np.zeros_like(f), *c.fwd, *c.bwd, c.h, c.ni, c.nj, c.nk, False]
+    _three_way("gpu_compensate_field", args,
+               lambda a: oracle.gpu_compensate(a[0], a[1], a[2], a[3:6], a[6:9], c.h, c.ni, c.nj, c.nk, "c"),
+               ours, ref, [0, 1, 2])
+
+
+@pytest.mark.parametrize("coeff", [1.0, 2.0])
+def test_accumulate_velocity(case, oracle, ours, ref, coeff):
+    c = case
+    f, g = c.fields, c.fields2
+    args = [f["u"], f["v"], f["w"], g["u"], g["v"], g["w"], *c.fwd, c.h, c.ni, c.nj, c.nk, False, coeff]
+
+    def run(a):
+        for q, kind in enumerate("uvw"):
+            oracle.cumulate(a[q], a[3 + q], a[6:9], c.h, c.ni, c.nj, c.nk, kind, coeff)
+
+    _three_way("gpu_accumulate_velocity", args, run, ours, ref, [3, 4, 5])
+
+
+def test_accumulate_field(case, oracle, ours, ref):
+    c = case
+    f, g = c.fields["c"], c.fields2["c"]
+    args = [f, g, *c.fwd, c.h, c.ni, c.nj, c.nk, False, 1.0]
+    _three_way("gpu_accumulate_field", args,
+               lambda a: oracle.cumulate(a[0], a[1], a[2:5], c.h, c.ni, c.nj, c.nk, "c", 1.0), ours, ref, [1])
+
+
+def test_advect_vel_double(case, oracle, ours, ref):
+    c = case
+    f, g = c.fields, c.fields2
+    args = [f["u"], f["v"], f["w"], g["u"], g["v"], g["w"], *c.bwd, *c.bwd_prev, c.h, c.ni, c.nj, c.nk, False, 0.5]
+
+    def run(a):
+        for q, kind in enumerate("uvw"):
+            oracle.double_advect(a[q], a[3 + q], a[6:9], a[9:12], c.h, c.ni, c.nj, c.nk, kind, 0.5)
+
+    _three_way("gpu_advect_vel_double", args, run, ours, ref, [0, 1, 2])
+
+
+def test_advect_field_double(case, oracle, ours, ref):
+    c = case
+    f, g = c.fields["c"], c.fields2["c"]
+    args = [f, g, *c.bwd, *c.bwd_prev, c.h, c.ni, c.nj, c.nk, False, 0.25]
+    _three_way("gpu_advect_field_double", args,
+               lambda a: oracle.double_advect(a[0], a[1], a[2:5], a[5:8], c.h, c.ni, c.nj, c.nk, "c", 0.25),
+               ours, ref, [0])
+
+
+def test_estimate_distortion(case, oracle, ours, ref):
+    c = case
+    d = np.zeros_like(c.fields["c"])
+    args = [d, *c.bwd, *c.fwd, c.h, c.ni, c.nj, c.nk]
+    _three_way("gpu_estimate_distortion", args,
+               lambda a: oracle.estimate(a[0], a[1:4], a[4:7], c.h, c.ni, c.nj, c.nk), ours, ref, [0])
+
+
+def test_add_and_add_field(case, oracle, ours, ref):
+    c = case
+    a, b = c.fields["c"], c.fields2["c"]
+    n = a.size
+    want = a - 0.5 * b
+    got = run_gpu_symbol(ours, "gpu_add", [a, b, -0.5, n])
+    assert rel_linf(got[0], want) <= 1e-6
+    got = run_gpu_symbol(ours, "gpu_add_field", [np.zeros_like(a), a, b, -1.0, n])
+    assert np.array_equal(got[0], a - b)
