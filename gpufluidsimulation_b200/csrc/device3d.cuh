@@ -108,9 +108,58 @@ __device__ __forceinline__ float3 get_velocity(const Vel3 &vel, const Grid3 &g, 
     return r;
 }
 
+// ---- bit-exact variant of the reference sampler, used ONLY where the reference's own formula
+// amplifies last-ulp differences: the DMC update computes 1 - exp(-a*s) in fp32
+// (GPU_kernel.cu:194-196), so one ulp of the velocity samples that form `a` can move the
+// back-traced point by up to ~6e-8/(a*s) of a cell.  To stay within tolerance of the reference
+// there, the two velocity evaluations of the DMC kernel reproduce the reference lerp exactly
+// as nvcc compiles it: (double)(1.0 - c) * a + (double)(float)(c*b), one double fma, rounded
+// to float.  (When h is a power of two the fractions at grid points are exactly 0 or 1/2 and
+// the fp32 lerp is already bit-identical, so the P2 path does not need this.)
+__device__ __forceinline__ float lerp_ref(float a, float b, float c)
+{
+    return __double2float_rn(__fma_rn(__dsub_rn(1.0, (double)c), (double)a, (double)__fmul_rn(c, b)));
+}
+
+__device__ __forceinline__ float tri8_ref(const float *__restrict__ p, int sy, int sz, const Frac &x,
+                                          const Frac &y, const Frac &z)
+{
+    float v000 = __ldg(p), v001 = __ldg(p + 1);
+    float v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
+    float v100 = __ldg(p + sz), v101 = __ldg(p + sz + 1);
+    float v110 = __ldg(p + sz + sy), v111 = __ldg(p + sz + sy + 1);
+    float a0 = lerp_ref(v000, v001, x.f), a1 = lerp_ref(v010, v011, x.f);
+    float a2 = lerp_ref(v100, v101, x.f), a3 = lerp_ref(v110, v111, x.f);
+    return lerp_ref(lerp_ref(a0, a1, y.f), lerp_ref(a2, a3, y.f), z.f);
+}
+
+__device__ __forceinline__ float3 get_velocity_ref(const Vel3 &vel, const Grid3 &g, float px, float py, float pz)
+{
+    const float hh = 0.5f * g.h;
+    Frac x0 = split<false>(px, g.h, g.inv_h), x5 = split<false>(px + hh, g.h, g.inv_h);
+    Frac y0 = split<false>(py, g.h, g.inv_h), y5 = split<false>(py + hh, g.h, g.inv_h);
+    Frac z0 = split<false>(pz, g.h, g.inv_h), z5 = split<false>(pz + hh, g.h, g.inv_h);
+    float3 r;
+    {
+        int sy = g.ni + 1, sz = (g.ni + 1) * g.nj;
+        r.x = tri8_ref(vel.u + (x5.i + sy * y0.i + sz * z0.i), sy, sz, x5, y0, z0);
+    }
+    {
+        int sy = g.ni, sz = g.ni * (g.nj + 1);
+        r.y = tri8_ref(vel.v + (x0.i + sy * y5.i + sz * z0.i), sy, sz, x0, y5, z0);
+    }
+    {
+        int sy = g.ni, sz = g.ni * g.nj;
+        r.z = tri8_ref(vel.w + (x0.i + sy * y0.i + sz * z5.i), sy, sz, x0, y0, z5);
+    }
+    return r;
+}
+
 // traceRK3 (GPU_kernel.cu:74-90): Ralston RK3 with the reference's clamp band [h,(n-1)h].
-// c1,c2,c3 are rounded from double like the reference; the midpoints use one fused
-// multiply-add each (the reference forms them in double and rounds once).
+// c1,c2,c3 are rounded from double like the reference.  The reference forms the midpoints in
+// double, input + (0.5*dt)*v1 and input + (0.75*dt)*v2, and rounds once to float: 0.5*dt is
+// exact in fp32, so one fmaf gives the identical result; 0.75*dt is not, so that midpoint is
+// formed with one double fma (3 per sub-step; everything else stays fp32).
 template <bool P2>
 __device__ __forceinline__ float3 trace_rk3(const Vel3 &vel, const Grid3 &g, float dt, float3 p)
 {
@@ -118,10 +167,12 @@ __device__ __forceinline__ float3 trace_rk3(const Vel3 &vel, const Grid3 &g, flo
     const float c2 = (float)(3.0 / 9.0 * (double)dt);
     const float c3 = (float)(4.0 / 9.0 * (double)dt);
     const float hd = 0.5f * dt;
-    const float qd = (float)(0.75 * (double)dt);
+    const double qd = 0.75 * (double)dt;
     float3 v1 = get_velocity<P2>(vel, g, p.x, p.y, p.z);
     float3 v2 = get_velocity<P2>(vel, g, fmaf(hd, v1.x, p.x), fmaf(hd, v1.y, p.y), fmaf(hd, v1.z, p.z));
-    float3 v3 = get_velocity<P2>(vel, g, fmaf(qd, v2.x, p.x), fmaf(qd, v2.y, p.y), fmaf(qd, v2.z, p.z));
+    float3 v3 = get_velocity<P2>(vel, g, __double2float_rn(__fma_rn(qd, (double)v2.x, (double)p.x)),
+                                 __double2float_rn(__fma_rn(qd, (double)v2.y, (double)p.y)),
+                                 __double2float_rn(__fma_rn(qd, (double)v2.z, (double)p.z)));
     float3 o;
     o.x = fmaf(c3, v3.x, fmaf(c2, v2.x, fmaf(c1, v1.x, p.x)));
     o.y = fmaf(c3, v3.y, fmaf(c2, v2.y, fmaf(c1, v1.y, p.y)));

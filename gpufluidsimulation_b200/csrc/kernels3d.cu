@@ -86,11 +86,12 @@ k_dmc(Grid3 g, int kbeg, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float 
     const int idx = i + g.ni * (j + g.nj * k);
     const float h = g.h;
     const float px = h * (float)i, py = h * (float)j, pz = h * (float)k;
-    float3 v0 = get_velocity<P2>(vel, g, px, py, pz);
+    // bit-exact reference arithmetic for the two velocity samples (see lerp_ref in device3d.cuh)
+    float3 v0 = P2 ? get_velocity<true>(vel, g, px, py, pz) : get_velocity_ref(vel, g, px, py, pz);
     const float tx = v0.x > 0.f ? px - h : px + h;
     const float ty = v0.y > 0.f ? py - h : py + h;
     const float tz = v0.z > 0.f ? pz - h : pz + h;
-    float3 v1 = get_velocity<P2>(vel, g, tx, ty, tz);
+    float3 v1 = P2 ? get_velocity<true>(vel, g, tx, ty, tz) : get_velocity_ref(vel, g, tx, ty, tz);
     const float ax = (v0.x - v1.x) / (px - tx);
     const float ay = (v0.y - v1.y) / (py - ty);
     const float az = (v0.z - v1.z) / (pz - tz);

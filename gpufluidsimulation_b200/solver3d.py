@@ -67,14 +67,18 @@ class GpuMapper:
 class MapperBaseGPU:
     """Drop-in mirror of the reference MapperBaseGPU (Mapping.h:47-105)."""
 
-    def init(self, ni, nj, nk, h, coeff, mymapper: GpuMapper):
+    def init(self, ni, nj, nk, h, coeff, mymapper: GpuMapper, lib=None):
+        """``lib``: a ctypes handle exporting the legacy gpu_* symbols; defaults to libbimocq_b200.so.
+        (The parity tests pass the reference's own kernels, oracle/_ref/libref3d.so, to drive the
+        identical call sequence through both.)"""
         torch = _torch()
         self.CellNumberX, self.CellNumberY, self.CellNumberZ = ni, nj, nk
         self.CellSize = float(np.float32(h))
         self.BlendCoeff = float(coeff)
         self.TotalReinitCount = 0
         self.gpuSolver = mymapper
-        self.lib = load_library()
+        self._ours = lib is None
+        self.lib = load_library() if lib is None else _with_legacy_prototypes(lib)
         shp = field_shape(ni, nj, nk, "c")
         h32 = np.float32(h)
         # Mapping.cpp:310-324: Init = (float)i * CellSize
@@ -96,6 +100,10 @@ class MapperBaseGPU:
     def _dims(self):
         return self.CellSize, self.CellNumberX, self.CellNumberY, self.CellNumberZ
 
+    def _check(self, what):
+        if self._ours:
+            check_legacy(what)
+
     # Mapping.cpp:354-368 + gpuMapper::solveBackwardDMC (GPU_Advection.h:460-470)
     def updateBackward(self, velocityU, velocityV, velocityW, cfldt, dt):
         g = self.gpuSolver
@@ -109,7 +117,7 @@ class MapperBaseGPU:
                                            _dp(g.z_out), h, ni, nj, nk, float(substep))
             self.BackwardX.copy_(g.x_out); self.BackwardY.copy_(g.y_out); self.BackwardZ.copy_(g.z_out)
             T = np.float32(T + substep)
-        check_legacy("gpu_solve_backwardDMC")
+        self._check("gpu_solve_backwardDMC")
 
     # Mapping.cpp:370-373
     def updateForward(self, velocityU, velocityV, velocityW, cfldt, dt):
@@ -117,7 +125,7 @@ class MapperBaseGPU:
         self.lib.gpu_solve_forward(_dp(velocityU), _dp(velocityV), _dp(velocityW), _dp(self.ForwardX),
                                    _dp(self.ForwardY), _dp(self.ForwardZ), h, ni, nj, nk, float(np.float32(cfldt)),
                                    float(np.float32(dt)))
-        check_legacy("gpu_solve_forward")
+        self._check("gpu_solve_forward")
 
     # Mapping.cpp:347-352
     def updateMapping(self, velocityU, velocityV, velocityW, cfldt, dt):
@@ -147,7 +155,7 @@ class MapperBaseGPU:
                                 _dp(velocityWPrev), _dp(self.BackwardX), _dp(self.BackwardY), _dp(self.BackwardZ),
                                 _dp(self.BackwardXPrev), _dp(self.BackwardYPrev), _dp(self.BackwardZPrev), h, ni, nj,
                                 nk, False, blend)
-        check_legacy("advectVelocity")
+        self._check("advectVelocity")
 
     # Mapping.cpp:393-407
     def advectField(self, field, fieldInit, fieldPrev):
@@ -165,7 +173,7 @@ class MapperBaseGPU:
         L.gpu_advect_field_double(_dp(field), _dp(fieldPrev), _dp(self.BackwardX), _dp(self.BackwardY),
                                   _dp(self.BackwardZ), _dp(self.BackwardXPrev), _dp(self.BackwardYPrev),
                                   _dp(self.BackwardZPrev), h, ni, nj, nk, False, blend)
-        check_legacy("advectField")
+        self._check("advectField")
 
     # Mapping.cpp:420-423 (argument order of the definition: init buffers first)
     def accumulateVelocity(self, duInit, dvInit, dwInit, uChange, vChange, wChange, coeff):
@@ -173,14 +181,14 @@ class MapperBaseGPU:
         self.lib.gpu_accumulate_velocity(_dp(uChange), _dp(vChange), _dp(wChange), _dp(duInit), _dp(dvInit),
                                          _dp(dwInit), _dp(self.ForwardX), _dp(self.ForwardY), _dp(self.ForwardZ), h,
                                          ni, nj, nk, False, float(coeff))
-        check_legacy("accumulateVelocity")
+        self._check("accumulateVelocity")
 
     # Mapping.cpp:425-428
     def accumulateField(self, dfieldInit, fieldChange):
         h, ni, nj, nk = self._dims()
         self.lib.gpu_accumulate_field(_dp(fieldChange), _dp(dfieldInit), _dp(self.ForwardX), _dp(self.ForwardY),
                                       _dp(self.ForwardZ), h, ni, nj, nk, False, 1.0)
-        check_legacy("accumulateField")
+        self._check("accumulateField")
 
     # Mapping.cpp:495-519 (boundary: optional int8 tensor, cells == 2 are skipped)
     def estimateDistortion(self, boundary=None):
@@ -190,7 +198,7 @@ class MapperBaseGPU:
         g.du.zero_()
         self.lib.gpu_estimate_distortion(_dp(g.du), _dp(self.BackwardX), _dp(self.BackwardY), _dp(self.BackwardZ),
                                          _dp(self.ForwardX), _dp(self.ForwardY), _dp(self.ForwardZ), h, ni, nj, nk)
-        check_legacy("gpu_estimate_distortion")
+        self._check("gpu_estimate_distortion")
         d = g.du.reshape(-1)[: ni * nj * nk].view(nk, nj, ni)
         if boundary is not None:
             d = torch.where(boundary == 2, torch.zeros_like(d), d)
@@ -203,6 +211,14 @@ class MapperBaseGPU:
             getattr(self, "Backward" + ax + "Prev").copy_(getattr(self, "Backward" + ax))
             getattr(self, "Backward" + ax).copy_(init)
             getattr(self, "Forward" + ax).copy_(init)
+
+
+def _with_legacy_prototypes(lib):
+    for name, (res, args) in capi._PROTOS.items():
+        if name.startswith("gpu_"):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    return lib
 
 
 class _DevView:

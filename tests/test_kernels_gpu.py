@@ -37,26 +37,42 @@ def ref(cuda):
     return lib
 
 
-def _check(name, got, want, tol=TOL_STEP):
-    for idx, (g, w) in enumerate(zip(got, want)):
-        err = rel_linf(g, w)
-        assert np.isfinite(g).all(), f"{name}: output {idx} has non-finite values"
-        assert err <= tol, f"{name}: output {idx} rel Linf {err:.3e} > {tol:.1e}"
+def _errs(got, want):
+    out = []
+    for g, w in zip(got, want):
+        assert np.isfinite(g).all(), "non-finite values in an output"
+        out.append(rel_linf(g, w))
+    return max(out)
 
 
-def _three_way(name, args, oracle_fn, ours, ref, outputs):
+# The reference's DMC update evaluates 1 - exp(-a*s) in fp32 (GPU_kernel.cu:194-196): for small a*s
+# one ulp of expf is a relative error of 6e-8/(a*s) in the back-traced displacement.  CUDA's expf
+# (MUFU.EX2 based) and glibc's differ in that last ulp, so a CPU oracle cannot track the reference's
+# DMC kernel to 1e-5; the GPU library can, and must (same expf, bit-identical velocity samples).
+TOL_ORACLE_DMC = 5e-4
+
+
+def _three_way(name, args, oracle_fn, ours, ref, outputs, tol_oracle=TOL_STEP):
     """Run on the oracle, our library and the reference library; compare the arrays at `outputs`
-    (indices into the array-only list)."""
+    (indices into the array-only list).  Parity bar: ours vs the reference kernels <= TOL_STEP."""
     arrays = [a for a in args if isinstance(a, np.ndarray)]
     from oracle import oracle3d as o3
     o_arrays = [o3.padded_copy(a) for a in arrays]
     oracle_fn(o_arrays)
     mine = run_gpu_symbol(ours, name, args)
-    _check(name + " vs oracle", [mine[i] for i in outputs], [o_arrays[i] for i in outputs])
+    e_mo = _errs([mine[i] for i in outputs], [o_arrays[i] for i in outputs])
+    msg = f"{name}: ours-vs-oracle {e_mo:.2e}"
     if ref is not None:
         theirs = run_gpu_symbol(ref, name, args)
-        _check(name + " vs reference kernel", [mine[i] for i in outputs], [theirs[i] for i in outputs])
-        _check(name + ": oracle vs reference kernel", [o_arrays[i] for i in outputs], [theirs[i] for i in outputs])
+        e_mr = _errs([mine[i] for i in outputs], [theirs[i] for i in outputs])
+        e_or = _errs([o_arrays[i] for i in outputs], [theirs[i] for i in outputs])
+        msg += f", ours-vs-reference-kernel {e_mr:.2e}, oracle-vs-reference-kernel {e_or:.2e}"
+        print(msg)
+        assert e_mr <= TOL_STEP, msg
+        assert e_or <= tol_oracle, msg
+    else:
+        print(msg)
+    assert e_mo <= tol_oracle, msg
 
 
 def test_solve_forward(case, oracle, ours, ref):
@@ -71,7 +87,8 @@ def test_solve_backward_dmc(case, oracle, ours, ref):
     out = [np.zeros_like(m) for m in c.bwd]
     args = [c.u, c.v, c.w, *c.bwd, *out, c.h, c.ni, c.nj, c.nk, 0.7 * c.cfldt]
     _three_way("gpu_solve_backwardDMC", args,
-               lambda a: oracle.gpu_solve_backwardDMC(*a, c.h, c.ni, c.nj, c.nk, 0.7 * c.cfldt), ours, ref, [6, 7, 8])
+               lambda a: oracle.gpu_solve_backwardDMC(*a, c.h, c.ni, c.nj, c.nk, 0.7 * c.cfldt), ours, ref, [6, 7, 8],
+               tol_oracle=TOL_ORACLE_DMC)
 
 
 @pytest.mark.parametrize("kind", ["u", "w", "c"])
