@@ -67,6 +67,8 @@ FIELD = {n: i for i, n in enumerate(FIELD_NAMES)}
 FIELD.update({n: 64 + i for i, n in enumerate(
     ["U_ADV", "V_ADV", "W_ADV", "RHO_ADV", "T_ADV", "U_ERR", "V_ERR", "W_ERR", "RHO_ERR", "T_ERR"])})
 
+N_TIMING_SLOTS = 16
+
 _PROTOS = {
     "bmq_last_error": (C.c_char_p, []),
     "bmq_clear_error": (_I, []),
@@ -97,6 +99,9 @@ _PROTOS = {
     "bmq3d_advect": (_I, [_H, _I, _f, _I]),
     "bmq3d_accumulate": (_I, [_H, _I, _f]),
     "bmq3d_get_stats": (_I, [_H, C.POINTER(Stats3D)]),
+    "bmq3d_timing_enable": (_I, [_H, _I]),
+    "bmq3d_timing_read": (_I, [_H, _F, C.POINTER(_I), _I]),
+    "bmq3d_timing_slot_name": (C.c_char_p, [_I]),
     "bmq3d_advect_host": (_I, [_H, _I, _f] + [C.c_void_p] * 5),
     "bmq3d_accumulate_host": (_I, [_H, _I, _f] + [C.c_void_p] * 8),
     "bmq3d_stage_maxvel": (_I, [_H, C.POINTER(_f)]),

@@ -55,6 +55,11 @@ struct bmq3d_solver {
     bool vel_reinit = false, scalar_reinit = false;
     bmq3d_stats stats;
     bool semi_alloc = false;
+    // optional per-stage CUDA-event timing (bmq3d_timing_*): pairs recorded on `stream`
+    bool timing = false;
+    struct Span { int slot; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
 };
 
 namespace {
@@ -132,10 +137,38 @@ int copy_field(bmq3d_solver *s, Field &dst, const Field &src)
     return BMQ_OK;
 }
 
+// ---- per-stage timing ----------------------------------------------------------------------
+const char *const kSlotNames[BMQ_T_COUNT] = {
+    "maxvel", "dmc_backward", "forward", "semilag", "advect_velocity", "error_velocity", "apply_velocity",
+    "blend_velocity", "advect_scalars", "error_scalars", "apply_scalars", "blend_scalars", "distortion",
+    "accumulate_velocity", "accumulate_scalars", "reinit"};
+
+cudaEvent_t take_event(bmq3d_solver *s)
+{
+    cudaEvent_t e = nullptr;
+    if (!s->event_pool.empty()) { e = s->event_pool.back(); s->event_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+struct StageTimer {
+    bmq3d_solver *s; int idx = -1;
+    StageTimer(bmq3d_solver *s_, int slot) : s(s_)
+    {
+        if (!s->timing) return;
+        bmq3d_solver::Span sp{slot, take_event(s), take_event(s)};
+        cudaEventRecord(sp.a, s->stream);
+        s->spans.push_back(sp);
+        idx = (int)s->spans.size() - 1;
+    }
+    ~StageTimer() { if (idx >= 0) cudaEventRecord(s->spans[idx].b, s->stream); }
+};
+
 // ---- stages ------------------------------------------------------------------------------
 
 int stage_maxvel(bmq3d_solver *s, float *out)
 {
+    StageTimer _t(s, BMQ_T_MAXVEL);
     BMQ_CK(cudaMemsetAsync(s->d_red, 0, sizeof(float), s->stream));
     // owned planes only, so a slab's halo copies are not double counted (harmless for a max anyway)
     const Field &u = s->f[BMQ_F_U], &v = s->f[BMQ_F_V], &w = s->f[BMQ_F_W];
@@ -162,6 +195,7 @@ void set_cfl(bmq3d_solver *s, int framenum, float max_abs)
 
 int stage_dmc(bmq3d_solver *s, float substep)
 {
+    StageTimer _t(s, BMQ_T_DMC);
     const float *const in[2][3] = {
         {s->f[BMQ_F_VBWD_X].vbase(), s->f[BMQ_F_VBWD_Y].vbase(), s->f[BMQ_F_VBWD_Z].vbase()},
         {s->f[BMQ_F_SBWD_X].vbase(), s->f[BMQ_F_SBWD_Y].vbase(), s->f[BMQ_F_SBWD_Z].vbase()}};
@@ -179,6 +213,7 @@ int stage_dmc(bmq3d_solver *s, float substep)
 
 int stage_forward(bmq3d_solver *s, float dt)
 {
+    StageTimer _t(s, BMQ_T_FORWARD);
     float *const maps[2][3] = {
         {s->f[BMQ_F_VFWD_X].vbase(), s->f[BMQ_F_VFWD_Y].vbase(), s->f[BMQ_F_VFWD_Z].vbase()},
         {s->f[BMQ_F_SFWD_X].vbase(), s->f[BMQ_F_SFWD_Y].vbase(), s->f[BMQ_F_SFWD_Z].vbase()}};
@@ -190,6 +225,7 @@ int stage_forward(bmq3d_solver *s, float dt)
 // BimocqSolver::semilagAdvect (BimocqSolver.cpp:645-668): traces back with -dt
 int stage_semilag(bmq3d_solver *s, float dt)
 {
+    StageTimer _t(s, BMQ_T_SEMILAG);
     int st = ensure_semi(s);
     if (st != BMQ_OK) return st;
     const float *u = s->f[BMQ_F_U].vbase(), *v = s->f[BMQ_F_V].vbase(), *w = s->f[BMQ_F_W].vbase();
@@ -213,6 +249,7 @@ void map_ptrs(bmq3d_solver *s, int first, const float *out[3])
 // which: 0 velocity (three staggered components, one launch each), 1 scalars (rho+T in one launch)
 int stage_advect(bmq3d_solver *s, int which)
 {
+    StageTimer _t(s, which == 0 ? BMQ_T_ADVECT_V : BMQ_T_ADVECT_S);
     const float *chi[3];
     if (which == 0) {
         map_ptrs(s, BMQ_F_VBWD_X, chi);
@@ -233,6 +270,7 @@ int stage_advect(bmq3d_solver *s, int which)
 
 int stage_error(bmq3d_solver *s, int which)
 {
+    StageTimer _t(s, which == 0 ? BMQ_T_ERROR_V : BMQ_T_ERROR_S);
     const float *psi[3];
     if (which == 0) {
         map_ptrs(s, BMQ_F_VFWD_X, psi);
@@ -255,6 +293,7 @@ int stage_error(bmq3d_solver *s, int which)
 
 int stage_apply(bmq3d_solver *s, int which)
 {
+    StageTimer _t(s, which == 0 ? BMQ_T_APPLY_V : BMQ_T_APPLY_S);
     const float *chi[3];
     if (which == 0) {
         map_ptrs(s, BMQ_F_VBWD_X, chi);
@@ -279,6 +318,7 @@ int stage_apply(bmq3d_solver *s, int which)
 // even with blend 1, where it computes f*1 + 0*p = f; that launch is skipped here.
 int stage_blend(bmq3d_solver *s, int which)
 {
+    StageTimer _t(s, which == 0 ? BMQ_T_BLEND_V : BMQ_T_BLEND_S);
     const int count = which == 0 ? s->vel_reinit_count : s->scalar_reinit_count;
     if (count == 0 || s->blend == 1.0f) return BMQ_OK;
     const float *chi[3], *chip[3];
@@ -304,6 +344,7 @@ int stage_blend(bmq3d_solver *s, int which)
 // estimateDistortion for both mappers (Mapping.cpp:91-118) with the max on the device
 int stage_distortion(bmq3d_solver *s, float *vel_d2, float *sca_d2, float *dispz)
 {
+    StageTimer _t(s, BMQ_T_DISTORTION);
     BMQ_CK(cudaMemsetAsync(s->d_red, 0, 4 * sizeof(float), s->stream));
     const float *const b[2][3] = {
         {s->f[BMQ_F_VBWD_X].vbase(), s->f[BMQ_F_VBWD_Y].vbase(), s->f[BMQ_F_VBWD_Z].vbase()},
@@ -346,6 +387,7 @@ void decide(bmq3d_solver *s, int framenum, float dt, float vel_d2, float sca_d2)
 // accumulate: init += 1*quad9[d_ext o psi] then += proj_coeff*quad9[d_proj o psi]  (BimocqSolver.cpp:193-196)
 int stage_accumulate(bmq3d_solver *s, int which)
 {
+    StageTimer _t(s, which == 0 ? BMQ_T_ACCUM_V : BMQ_T_ACCUM_S);
     const float *psi[3];
     if (which == 0) {
         map_ptrs(s, BMQ_F_VFWD_X, psi);
@@ -370,6 +412,7 @@ int stage_accumulate(bmq3d_solver *s, int which)
 // phase 1 (velocity only): the extra accumulate(duproj, 1.0) of BimocqSolver.cpp:214
 int stage_reinit(bmq3d_solver *s, int which, int phase)
 {
+    StageTimer _t(s, BMQ_T_REINIT);
     if (which == 0) {
         if (phase == 0) {
             s->vel_reinit_count++;
@@ -452,6 +495,8 @@ int bmq3d_destroy(bmq3d_solver *s)
     for (auto &fd : s->f) if (fd.alloc) cudaFree(fd.alloc);
     for (auto &fd : s->scratch) if (fd.alloc) cudaFree(fd.alloc);
     for (auto &fd : s->tmpmap) if (fd.alloc) cudaFree(fd.alloc);
+    for (auto &sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : s->event_pool) cudaEventDestroy(e);
     if (s->d_red) cudaFree(s->d_red);
     if (s->h_red) cudaFreeHost(s->h_red);
     delete s;
@@ -617,6 +662,34 @@ int bmq3d_accumulate(bmq3d_solver *s, int framenum, float dt)
     if (s->scalar_reinit) RET_IF(stage_reinit(s, 1, 0));
     s->stats.vel_reinit_count = s->vel_reinit_count;
     s->stats.scalar_reinit_count = s->scalar_reinit_count;
+    return BMQ_OK;
+}
+
+int bmq3d_timing_enable(bmq3d_solver *s, int on)
+{
+    NEED(s);
+    s->timing = on != 0;
+    return BMQ_OK;
+}
+
+const char *bmq3d_timing_slot_name(int slot) { return slot >= 0 && slot < BMQ_T_COUNT ? kSlotNames[slot] : ""; }
+
+// Sums the recorded spans per slot (synchronises the stream), returns them and clears the record.
+int bmq3d_timing_read(bmq3d_solver *s, float *ms_out, int *spans_out, int n_slots)
+{
+    NEED(s);
+    if (!ms_out || n_slots < BMQ_T_COUNT) return set_error(BMQ_ERR_ARG, "bmq3d_timing_read: need %d slots", (int)BMQ_T_COUNT);
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    for (int q = 0; q < n_slots; ++q) { ms_out[q] = 0.f; if (spans_out) spans_out[q] = 0; }
+    for (auto &sp : s->spans) {
+        float ms = 0.f;
+        BMQ_CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ms_out[sp.slot] += ms;
+        if (spans_out) spans_out[sp.slot]++;
+        s->event_pool.push_back(sp.a);
+        s->event_pool.push_back(sp.b);
+    }
+    s->spans.clear();
     return BMQ_OK;
 }
 

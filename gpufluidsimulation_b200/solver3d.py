@@ -289,6 +289,28 @@ class BimocqAdvection3D:
     def reset(self):
         check(self.lib.bmq3d_reset(self._h), "bmq3d_reset")
 
+    def set_initial_device(self, u, v, w, rho, T):
+        """Initial fields given as device tensors (whole grid)."""
+        for n, a in zip(self.CURRENT, (u, v, w, rho, T)):
+            self.field(n).copy_(a)
+        _torch().cuda.synchronize()
+        self.reset()
+
+    def apply_buoyancy(self, beta, dt, alpha=0.0):
+        """Caller stand-in used by the benchmark between the two phases (NOT part of the hot
+        path): the reference's buoyancy (GPU_kernel.cu:804-823), dv = dt*(-alpha*rho + beta*T)
+        averaged onto the v faces, written to DV_EXT and added to V; the other change fields
+        stay zero."""
+        torch = _torch()
+        T, dv, V = self.field("T"), self.field("DV_EXT"), self.field("V")
+        inner = dv[:, 1:-1, :]
+        torch.add(T[:, 1:, :], T[:, :-1, :], out=inner)
+        inner.mul_(0.5 * dt * beta)
+        if alpha:
+            rho = self.field("RHO")
+            inner.add_(rho[:, 1:, :] + rho[:, :-1, :], alpha=-0.5 * dt * alpha)
+        V.add_(dv)
+
     def advect(self, framenum, dt, with_semilag=False):
         check(self.lib.bmq3d_advect(self._h, int(framenum), float(np.float32(dt)), int(with_semilag)), "bmq3d_advect")
 
@@ -310,6 +332,16 @@ class BimocqAdvection3D:
         st = Stats3D()
         check(self.lib.bmq3d_get_stats(self._h, C.byref(st)), "bmq3d_get_stats")
         return st.as_dict()
+
+    def timing_enable(self, on=True):
+        check(self.lib.bmq3d_timing_enable(self._h, int(on)), "bmq3d_timing_enable")
+
+    def timing_read(self):
+        """{stage name: (milliseconds, spans)} since the last read (synchronises the stream)."""
+        n = capi.N_TIMING_SLOTS
+        ms = (C.c_float * n)(); cnt = (C.c_int * n)()
+        check(self.lib.bmq3d_timing_read(self._h, ms, cnt, n), "bmq3d_timing_read")
+        return {self.lib.bmq3d_timing_slot_name(q).decode(): (ms[q], cnt[q]) for q in range(n)}
 
     # fine-grained stages (z-slab driver)
     def stage(self, name, *args):

@@ -168,6 +168,16 @@ int bmq3d_advect(bmq3d_solver *s, int framenum, float dt, int with_semilag);
 int bmq3d_accumulate(bmq3d_solver *s, int framenum, float dt);
 int bmq3d_get_stats(bmq3d_solver *s, bmq3d_stats *out);
 
+/* Optional per-stage timing with CUDA events recorded on the solver's stream (used by bench.py
+ * for the live roofline number).  bmq3d_timing_read synchronises, writes the milliseconds and
+ * the number of recorded spans per slot (arrays of BMQ_T_COUNT), and clears the record. */
+enum { BMQ_T_MAXVEL = 0, BMQ_T_DMC, BMQ_T_FORWARD, BMQ_T_SEMILAG, BMQ_T_ADVECT_V, BMQ_T_ERROR_V,
+       BMQ_T_APPLY_V, BMQ_T_BLEND_V, BMQ_T_ADVECT_S, BMQ_T_ERROR_S, BMQ_T_APPLY_S, BMQ_T_BLEND_S,
+       BMQ_T_DISTORTION, BMQ_T_ACCUM_V, BMQ_T_ACCUM_S, BMQ_T_REINIT, BMQ_T_COUNT };
+int bmq3d_timing_enable(bmq3d_solver *s, int on);
+int bmq3d_timing_read(bmq3d_solver *s, float *ms_out, int *spans_out, int n_slots);
+const char *bmq3d_timing_slot_name(int slot);
+
 /* Whole step through HOST buffers (the reference's host-orchestrated solver keeps its fields on
  * the host, Mapping.cpp:7-236).  bmq3d_advect_host uploads u,v,w,rho,T, runs phase A and
  * downloads the advected fields into the same arrays.  The caller then applies its forces and

@@ -1,0 +1,82 @@
+"""Pins the CPU oracle against golden outputs of THE REFERENCE'S OWN CUDA KERNELS
+(tests/golden/ref3d_kernels.npz, produced on a B200 by tests/golden/make_golden_3d.py from
+oracle/_ref/libref3d.so).  The inputs are regenerated from their seed (the generator's Case3D),
+the outputs must match: bit-for-bit tolerance 2e-7 (rel L-inf) for every kernel except the DMC
+update, where glibc's and CUDA's expf differ in the last ulp (see tests/test_kernels_gpu.py)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from helpers import Case3D, rel_linf
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "ref3d_kernels.npz")
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("make_golden_3d", os.path.join(HERE, "golden", "make_golden_3d.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def setup(oracle):
+    if not os.path.exists(GOLD):
+        pytest.skip("golden file not generated yet")
+    m = _gen()
+    c = Case3D(m.NI, m.NJ, m.NK, m.H, seed=11)
+    return m, c, np.load(GOLD)
+
+
+def _run_oracle(o3, name, arrays, c):
+    A = [o3.padded_copy(a) for a in arrays]
+    d = (c.h, c.ni, c.nj, c.nk)
+    if name == "gpu_solve_forward":
+        o3.gpu_solve_forward(*A, *d, c.cfldt, c.dt)
+    elif name == "gpu_solve_backwardDMC":
+        o3.gpu_solve_backwardDMC(*A, *d, 0.7 * c.cfldt)
+    elif name == "gpu_semilag":
+        o3.gpu_semilag(*A, 0, 1, 0, *d, c.cfldt, -c.dt)
+    elif name == "gpu_advect_velocity":
+        for q, k in enumerate("uvw"):
+            o3.advect(A[q], A[3 + q], A[6], A[7], A[8], *d, k)
+    elif name == "gpu_advect_field":
+        o3.advect(A[0], A[1], A[2], A[3], A[4], *d, "c")
+    elif name == "gpu_compensate_velocity":
+        for q, k in enumerate("uvw"):
+            o3.gpu_compensate(A[q], A[3 + q], A[6 + q], A[9:12], A[12:15], *d, k)
+    elif name == "gpu_compensate_field":
+        o3.gpu_compensate(A[0], A[1], A[2], A[3:6], A[6:9], *d, "c")
+    elif name == "gpu_accumulate_velocity":
+        for q, k in enumerate("uvw"):
+            o3.cumulate(A[q], A[3 + q], A[6:9], *d, k, 2.0)
+    elif name == "gpu_accumulate_field":
+        o3.cumulate(A[0], A[1], A[2:5], *d, "c", 1.0)
+    elif name == "gpu_advect_vel_double":
+        for q, k in enumerate("uvw"):
+            o3.double_advect(A[q], A[3 + q], A[6:9], A[9:12], *d, k, 0.5)
+    elif name == "gpu_advect_field_double":
+        o3.double_advect(A[0], A[1], A[2:5], A[5:8], *d, "c", 0.25)
+    elif name == "gpu_estimate_distortion":
+        o3.estimate(A[0], A[1:4], A[4:7], *d)
+    else:
+        raise KeyError(name)
+    return A
+
+
+def test_oracle_matches_reference_kernel_golden_vectors(setup, oracle):
+    m, c, gold = setup
+    seen = 0
+    for name, (args, outs) in m.calls(c).items():
+        arrays = [a for a in args if isinstance(a, np.ndarray)]
+        A = _run_oracle(oracle, name, arrays, c)
+        tol = 5e-4 if name == "gpu_solve_backwardDMC" else 2e-7
+        for q in outs:
+            want = gold[f"{name}:out{q}"]
+            err = rel_linf(A[q], want)
+            assert err <= tol, (name, q, err)
+            seen += 1
+    assert seen == len(gold.files)
