@@ -274,6 +274,121 @@ __device__ __forceinline__ void quad_gather(const Map3 &m, const Grid3 &g, float
     sample_fields<P2, NS>(src, fnx, fny, g, ox, oy, oz, mp.x, mp.y, mp.z, value);
 }
 
+// ---- windowed quadrature ---------------------------------------------------------------------
+// The eight sub-cell points of an output cell sit at +-h/4 around a grid-aligned position, so
+// on every axis their map samples use one of two (cell, fraction) pairs and all of them read
+// from one 3x3x3 (2 on the staggered axis) window of map nodes around the cell.  The reference
+// fetches 9 x 8 nodes per map component (GPU_kernel.cu:350-352); here the window is loaded once
+// (27 or 18 loads) and the 8 trilinear samples are evaluated separably -- 18 x-lerps, 12
+// y-lerps, 8 z-lerps, each the SAME fmaf(1-f, a, f*b) on the same operands in the same x->y->z
+// order as eight independent trilerps, so the results are bit-identical to them.
+//   axis geometry (cell index c, window base c-1):   minus point        plus point       centre
+//     unstaggered axis (pos = c h):                 cell c-1, f~3/4    cell c,   f~1/4   cell c,   f~0
+//     staggered axis   (pos = (c-1/2) h):           cell c-1, f~1/4    cell c-1, f~3/4   cell c-1, f~1/2
+// The fractions are computed with the reference's expression (position/h - floor) unless h is
+// a power of two, where they are exactly the constants above.  floor() of the +-1/4 points is
+// structurally safe (they are 1/4 cell away from an integer); the centre point's floor is not
+// (c h / h may round below c), so without P2 the centre sample uses the generic 8-node path.
+template <bool P2, bool STAGGERED>
+struct AxisW {
+    float fm, om, fp, op;   // minus / plus fractions and their complements
+    __device__ __forceinline__ void init(float c_pos, float h, float inv_h)
+    {
+        if (P2) {
+            fm = STAGGERED ? 0.25f : 0.75f;
+            fp = STAGGERED ? 0.75f : 0.25f;
+        } else {
+            const float q = 0.25f * h;
+            const float qm = __fdiv_rn(c_pos - q, h), qp = __fdiv_rn(c_pos + q, h);
+            fm = qm - floorf(qm);
+            fp = qp - floorf(qp);
+        }
+        om = 1.0f - fm;
+        op = 1.0f - fp;
+    }
+};
+
+// 8 corner samples (index = reference order ii: x sign bit 2, y sign bit 1, z sign bit 0; 0 = plus)
+// and, when P2, the centre sample of ONE map component from its node window.
+// `p` points at node (i-1, j-1, k-1) of the component array.
+template <bool P2, int STAG>
+__device__ __forceinline__ void window_samples(const float *__restrict__ p, int sy, int sz,
+                                               const AxisW<P2, STAG == 1> &ax, const AxisW<P2, STAG == 2> &ay,
+                                               const AxisW<P2, STAG == 3> &az, float (&out)[8], float &centre)
+{
+    constexpr int NX = STAG == 1 ? 2 : 3, NY = STAG == 2 ? 2 : 3, NZ = STAG == 3 ? 2 : 3;
+    float Y[NZ][2][2];   // [z node][y sign][x sign]   (sign index 0 = plus, 1 = minus)
+    float cyz[NZ];       // centre-line values per z node (P2 only)
+#pragma unroll
+    for (int z = 0; z < NZ; ++z) {
+        float X[NY][2];
+        float xc[NY];
+#pragma unroll
+        for (int y = 0; y < NY; ++y) {
+            const float *r = p + y * sy + z * sz;
+            const float n0 = __ldg(r), n1 = __ldg(r + 1);
+            const float n2 = NX == 3 ? __ldg(r + 2) : 0.f;
+            X[y][1] = lerp32(n0, n1, ax.fm, ax.om);
+            X[y][0] = NX == 3 ? lerp32(n1, n2, ax.fp, ax.op) : lerp32(n0, n1, ax.fp, ax.op);
+            if (P2) xc[y] = NX == 3 ? n1 : lerp32(n0, n1, 0.5f, 0.5f);
+        }
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx) {
+            Y[z][1][sx] = lerp32(X[0][sx], X[1][sx], ay.fm, ay.om);
+            Y[z][0][sx] = NY == 3 ? lerp32(X[1][sx], X[2][sx], ay.fp, ay.op) : lerp32(X[0][sx], X[1][sx], ay.fp, ay.op);
+        }
+        if (P2) cyz[z] = NY == 3 ? xc[1] : lerp32(xc[0], xc[1], 0.5f, 0.5f);
+    }
+#pragma unroll
+    for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+        for (int sy_ = 0; sy_ < 2; ++sy_) {
+            out[sx * 4 + sy_ * 2 + 1] = lerp32(Y[0][sy_][sx], Y[1][sy_][sx], az.fm, az.om);
+            out[sx * 4 + sy_ * 2 + 0] =
+                NZ == 3 ? lerp32(Y[1][sy_][sx], Y[2][sy_][sx], az.fp, az.op) : lerp32(Y[0][sy_][sx], Y[1][sy_][sx], az.fp, az.op);
+        }
+    if (P2) centre = NZ == 3 ? cyz[1] : lerp32(cyz[0], cyz[1], 0.5f, 0.5f);
+}
+
+// Windowed version of quad_gather for the 8-point quadrature (is_point == false).
+// (i,j,k) is the output cell in its own (staggered) array; (cx,cy,cz) its world position.
+template <bool P2, int STAG, int NS>
+__device__ __forceinline__ void quad_gather_win(const Map3 &m, const Grid3 &g, int i, int j, int k, float cx,
+                                                float cy, float cz, float lo, float hix, float hiy, float hiz,
+                                                const float *const (&src)[NS], int fnx, int fny, float ox,
+                                                float oy, float oz, const float (&wgt)[NS], float (&sum)[NS],
+                                                float (&value)[NS])
+{
+    AxisW<P2, STAG == 1> ax;
+    AxisW<P2, STAG == 2> ay;
+    AxisW<P2, STAG == 3> az;
+    ax.init(cx, g.h, g.inv_h);
+    ay.init(cy, g.h, g.inv_h);
+    az.init(cz, g.h, g.inv_h);
+    const int sy = g.ni, sz = g.ni * g.nj;
+    const int base = (i - 1) + sy * (j - 1) + sz * (k - 1);
+    float px[8], py[8], pz[8], ccx, ccy, ccz;
+    window_samples<P2, STAG>(m.x + base, sy, sz, ax, ay, az, px, ccx);
+    window_samples<P2, STAG>(m.y + base, sy, sz, ax, ay, az, py, ccy);
+    window_samples<P2, STAG>(m.z + base, sy, sz, ax, ay, az, pz, ccz);
+    if (!P2) {
+        float3 c = sample_map<false>(m, g, cx, cy, cz);
+        ccx = c.x; ccy = c.y; ccz = c.z;
+    }
+#pragma unroll
+    for (int f = 0; f < NS; ++f) sum[f] = 0.f;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+        float s[NS];
+        sample_fields<P2, NS>(src, fnx, fny, g, ox, oy, oz, clampf(px[ii], lo, hix), clampf(py[ii], lo, hiy),
+                              clampf(pz[ii], lo, hiz), s);
+#pragma unroll
+        for (int f = 0; f < NS; ++f) sum[f] = fmaf(wgt[f], s[f], sum[f]);
+    }
+    sample_fields<P2, NS>(src, fnx, fny, g, ox, oy, oz, clampf(ccx, lo, hix), clampf(ccy, lo, hiy),
+                          clampf(ccz, lo, hiz), value);
+}
+
 // ---- reductions -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v)
 {

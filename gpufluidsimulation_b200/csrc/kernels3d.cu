@@ -259,6 +259,114 @@ k_apply_clamp(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, Fie
     for (int f = 0; f < NF; ++f) out.p[f][idx] = r[f];
 }
 
+// ------------------------------------------------------------------ windowed 8-point variants
+// Same arithmetic as k_advect / k_error / k_cumulate / k_apply_clamp with is_point == false, but
+// the map samples of the 8 sub-cell points come from one node window per map component
+// (quad_gather_win in device3d.cuh).  STAG: 0 centred, 1/2/3 = u/v/w faces (compile time).
+#define BMQ_STAG_SETUP                                                                             \
+    constexpr int DX = STAG == 1, DY = STAG == 2, DZ = STAG == 3;                                  \
+    const int fi = g.ni + DX, fj = g.nj + DY, fk = g.nk + DZ;                                      \
+    (void)fk;                                                                                      \
+    BMQ_IJK(fi, fj)                                                                                \
+    const float h = g.h;                                                                           \
+    const float ox = -(float)DX * 0.5f * h, oy = -(float)DY * 0.5f * h, oz = -(float)DZ * 0.5f * h; \
+    const float cx = fmaf(h, (float)i, ox), cy = fmaf(h, (float)j, oy), cz = fmaf(h, (float)k, oz); \
+    const int idx = i + fi * (j + fj * k);
+
+template <bool P2, int STAG, int NF>
+__global__ void __launch_bounds__(256)
+k_advect_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
+{
+    BMQ_STAG_SETUP
+    if (!(2 + DX < i && i < fi - 3 && 2 + DY < j && j < fj - 3 && 2 + DZ < k && k < fk - 3)) return;
+    float sum[NF], val[NF], wgt[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) wgt[f] = 0.125f;
+    quad_gather_win<P2, STAG, NF>(chi, g, i, j, k, cx, cy, cz, h, h * (float)g.ni - h, h * (float)g.nj - h,
+                                  h * (float)g.nk - h, init.p, fi, fj, ox, oy, oz, wgt, sum, val);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out.p[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]);
+}
+
+template <bool P2, int STAG, int NF>
+__global__ void __launch_bounds__(256)
+k_error_win(Grid3 g, int kbeg, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
+{
+    BMQ_STAG_SETUP
+    if (!(1 + DX < i && i < fi - 2 && 1 + DY < j && j < fj - 2 && 1 + DZ < k && k < fk - 2)) return;
+    float sum[NF], val[NF], wgt[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) wgt[f] = 0.125f;
+    quad_gather_win<P2, STAG, NF>(psi, g, i, j, k, cx, cy, cz, 0.f, h * (float)g.ni, h * (float)g.nj, h * (float)g.nk,
+                                  src.p, fi, fj, ox, oy, oz, wgt, sum, val);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) e0.p[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]) - __ldg(init.p[f] + idx);
+}
+
+template <bool P2, int STAG, int NF, int NCH>
+__global__ void __launch_bounds__(256)
+k_cumulate_win(Grid3 g, int kbeg, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change, Coeffs<NCH> coeff, Map3 map)
+{
+    BMQ_STAG_SETUP
+    if (!(1 + DX < i && i < fi - 2 && 1 + DY < j && j < fj - 2 && 1 + DZ < k && k < fk - 2)) return;
+    float sum[NF * NCH], val[NF * NCH], wgt[NF * NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) wgt[c * NF + f] = 0.125f * coeff.c[c];
+    quad_gather_win<P2, STAG, NF * NCH>(map, g, i, j, k, cx, cy, cz, 0.f, h * (float)g.ni, h * (float)g.nj,
+                                        h * (float)g.nk, change.p, fi, fj, ox, oy, oz, wgt, sum, val);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        float t = target.p[f][idx];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const float v = coeff.c[c] * val[c * NF + f];
+            t += fmaf(0.5f, sum[c * NF + f], 0.5f * v);
+        }
+        target.p[f][idx] = t;
+    }
+}
+
+template <bool P2, int STAG, int NF>
+__global__ void __launch_bounds__(256)
+k_apply_clamp_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> fadv, FieldSetRO<NF> e0, Map3 chi)
+{
+    BMQ_STAG_SETUP
+    float r[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) r[f] = __ldg(fadv.p[f] + idx);
+    if (1 + DX < i && i < fi - 2 && 1 + DY < j && j < fj - 2 && 1 + DZ < k && k < fk - 2) {
+        float sum[NF], val[NF], wgt[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) wgt[f] = 0.125f * -0.5f;
+        quad_gather_win<P2, STAG, NF>(chi, g, i, j, k, cx, cy, cz, 0.f, h * (float)g.ni, h * (float)g.nj,
+                                      h * (float)g.nk, e0.p, fi, fj, ox, oy, oz, wgt, sum, val);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) r[f] += fmaf(0.5f, sum[f], 0.5f * (-0.5f * val[f]));
+    }
+    if (i > 0 && i < fi - 1 && j > 0 && j < fj - 1 && k > 0 && k < fk - 1) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const float *b = fadv.p[f];
+            float mx = __ldg(b + idx), mn = mx;
+#pragma unroll
+            for (int kk = -1; kk <= 1; ++kk)
+#pragma unroll
+                for (int jj = -1; jj <= 1; ++jj)
+#pragma unroll
+                    for (int ii = -1; ii <= 1; ++ii) {
+                        const float v = __ldg(b + idx + ii + fi * (jj + fj * kk));
+                        mx = fmaxf(mx, v);
+                        mn = fminf(mn, v);
+                    }
+            r[f] = fminf(fmaxf(mn, r[f]), mx);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out.p[f][idx] = r[f];
+}
+
 // clampExtrema_kernel alone (legacy gpu_compensate_* keeps the reference's buffer contract)
 __global__ void __launch_bounds__(256)
 k_clamp_extrema(int fi, int fj, int fk, int kbeg, const float *__restrict__ before, float *after)
@@ -473,6 +581,21 @@ cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u,
     return cudaGetLastError();
 }
 
+
+// dispatch helpers: STAG (compile time) from the runtime staggering
+static inline int stag_id(Stag st) { return st.dx ? 1 : st.dy ? 2 : st.dz ? 3 : 0; }
+#define DISPATCH_STAG_P2(g, st, KERNEL, NFLIST, ...)                                            \
+    do {                                                                                        \
+        const bool p2_ = is_pow2_h(g);                                                          \
+        switch (stag_id(st)) {                                                                  \
+        case 0: if (p2_) KERNEL<true, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 1: if (p2_) KERNEL<true, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 2: if (p2_) KERNEL<true, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        default: if (p2_) KERNEL<true, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        }                                                                                       \
+    } while (0)
+#define COMMA ,
+
 template <int NF> static FieldSetRO<NF> ro(const float *const *p) { FieldSetRO<NF> f; for (int q = 0; q < NF; ++q) f.p[q] = p[q]; return f; }
 template <int NF> static FieldSetRW<NF> rw(float *const *p) { FieldSetRW<NF> f; for (int q = 0; q < NF; ++q) f.p[q] = p[q]; return f; }
 
@@ -493,12 +616,25 @@ cudaError_t launch_semilag(cudaStream_t s, const Grid3 &g, KRange r, Stag st, co
     return cudaGetLastError();
 }
 
+static void k_dispatch_centred2_advect(cudaStream_t s, const Grid3 &g, KRange r, dim3 gr, dim3 bl, float *const *out,
+                                       const float *const *init, Map3 m)
+{
+    if (is_pow2_h(g)) k_advect_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(init), m);
+    else k_advect_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(init), m);
+}
+
 cudaError_t launch_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
                           float *const *out, const float *const *init, const float *const chi[3])
 {
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{chi[0], chi[1], chi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0)) {
+        if (nf == 1) DISPATCH_STAG_P2(g, st, k_advect_win, 1, g, r.kbeg, rw<1>(out), ro<1>(init), m);
+        else k_dispatch_centred2_advect(s, g, r, gr, bl, out, init, m);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (nf == 1)
         DISPATCH_P2(g, (k_advect<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(init), m)),
                     (k_advect<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(init), m)));
@@ -516,6 +652,13 @@ cudaError_t launch_error(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{psi[0], psi[1], psi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0)) {
+        if (nf == 1) DISPATCH_STAG_P2(g, st, k_error_win, 1, g, r.kbeg, rw<1>(e0), ro<1>(src), ro<1>(init), m);
+        else if (is_pow2_h(g)) k_error_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(e0), ro<2>(src), ro<2>(init), m);
+        else k_error_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(e0), ro<2>(src), ro<2>(init), m);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (nf == 1)
         DISPATCH_P2(g, (k_error<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)),
                     (k_error<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)));
@@ -533,6 +676,21 @@ cudaError_t launch_cumulate(cudaStream_t s, const Grid3 &g, KRange r, Stag st, b
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{map[0], map[1], map[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0)) {
+        if (nf == 1 && nch == 1) {
+            Coeffs<1> c; c.c[0] = coeff[0];
+            DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 1, g, r.kbeg, rw<1>(target), ro<1>(change), c, m);
+        } else if (nf == 1 && nch == 2) {
+            Coeffs<2> c; c.c[0] = coeff[0]; c.c[1] = coeff[1];
+            DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 2, g, r.kbeg, rw<1>(target), ro<2>(change), c, m);
+        } else if (nf == 2 && nch == 1) {
+            Coeffs<1> c; c.c[0] = coeff[0];
+            if (is_pow2_h(g)) k_cumulate_win<true, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(target), ro<2>(change), c, m);
+            else k_cumulate_win<false, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(target), ro<2>(change), c, m);
+        } else return cudaErrorInvalidValue;
+        count_launch();
+        return cudaGetLastError();
+    }
 #define CUM(NF, NCH)                                                                                   \
     {                                                                                                  \
         Coeffs<NCH> c;                                                                                 \
@@ -556,6 +714,13 @@ cudaError_t launch_apply_clamp(cudaStream_t s, const Grid3 &g, KRange r, Stag st
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{chi[0], chi[1], chi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0)) {
+        if (nf == 1) DISPATCH_STAG_P2(g, st, k_apply_clamp_win, 1, g, r.kbeg, rw<1>(out), ro<1>(fadv), ro<1>(e0), m);
+        else if (is_pow2_h(g)) k_apply_clamp_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
+        else k_apply_clamp_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (nf == 1)
         DISPATCH_P2(g, (k_apply_clamp<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)),
                     (k_apply_clamp<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)));
