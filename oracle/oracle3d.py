@@ -64,7 +64,20 @@ def lib():
     return _LIB
 
 
-def _p(a: np.ndarray):
+class VirtualArray:
+    """A float* that points `offset_elems` floats BEFORE a numpy array: a z-slab rank hands the
+    oracle the address its plane 0 would have, so that all indices stay global (the CUDA
+    kernels get the same kind of virtual base, gpufluidsimulation_b200/csrc/kernels3d.cu)."""
+
+    def __init__(self, arr: np.ndarray, offset_elems: int):
+        assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"]
+        self.arr = arr
+        self.vaddr = arr.ctypes.data - 4 * int(offset_elems)
+
+
+def _p(a):
+    if isinstance(a, VirtualArray):
+        return C.cast(C.c_void_p(a.vaddr), _F)
     assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_F)
 
@@ -142,8 +155,8 @@ def compensate_kernel(src, temp, test, m, h, ni, nj, nk, kind, is_point=False, k
                         int(is_point), kb, ke)
 
 
-def clamp_extrema(before, after, krange=None):
-    nz, ny, nx = before.shape
+def clamp_extrema(before, after, krange=None, dims=None):
+    nz, ny, nx = dims or before.shape
     kb, ke = krange or (0, nz)
     lib().o3_clamp_extrema(_p(before), _p(after), nx, ny, nz, kb, ke)
 

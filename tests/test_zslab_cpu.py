@@ -1,0 +1,139 @@
+"""CPU tests of the z-slab decomposition logic (gpufluidsimulation_b200/zslab.py): partition and
+halo geometry, and -- over gloo with world_size 2 and 3 -- that the slab stepper driving
+oracle-backed ranks reproduces the single-domain oracle bit for bit (fields, maps, reinit frames)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from gpufluidsimulation_b200 import scenes, zslab
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_slab_bounds_cover_domain():
+    for nk in (16, 17, 50, 512):
+        for world in (1, 2, 3, 4, 8):
+            b = [zslab.slab_bounds(nk, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == nk
+            assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+            sizes = [k1 - k0 for k0, k1 in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_halo_plane_ranges_pair_up():
+    """What rank r sends up/down is exactly what rank r+1 / r-1 expects to receive."""
+    nk, world, width = 40, 4, 6
+    for name in ("RHO", "W", "U"):
+        for r in range(world):
+            k0, k1 = zslab.slab_bounds(nk, world, r)
+            lo, up, down, upsend = zslab.halo_planes(name, nk, k0, k1, world, r, width)
+            if r + 1 < world:
+                n0, n1 = zslab.slab_bounds(nk, world, r + 1)
+                nlo, _, ndown, _ = zslab.halo_planes(name, nk, n0, n1, world, r + 1, width)
+                assert upsend == nlo       # my top planes -> neighbour's lower halo
+                assert up == ndown         # neighbour's bottom planes -> my upper halo
+            else:
+                assert up is None and upsend is None
+            if r == 0:
+                assert lo is None and down is None
+
+
+def test_halo_too_narrow_is_loud():
+    class R:   # minimal stand-in
+        halo, nk, h, rank, k0, k1 = 4, 32, 1 / 32, 0, 0, 16
+    st = zslab.ZSlabStepper([R()], zslab.LocalComm(2))
+    st.disp = 7.3
+    with pytest.raises(zslab.HaloTooNarrow):
+        st._width(11)
+    assert st._width(4) == 4
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ni, nj, nk, halo, frames, blend, out_q):
+    sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle_slab_rank import OracleSlabRank
+    h = 1.0 / ni
+    dt = 0.02
+    full = list(scenes.smoke_plume(ni, nj, nk, 1.0))
+    full[:3] = scenes.scale_to_cfl(*full[:3], h, dt, 1.5)
+    full = [np.ascontiguousarray(a, dtype=np.float32) for a in full]
+    r = OracleSlabRank(ni, nj, nk, h, blend, rank, world, halo)
+    r.set_initial(full)
+    st = zslab.ZSlabStepper([r], zslab.DistComm(world, rank, torch.device("cpu")), blend)
+    log = []
+    for frame in range(frames):
+        st.advect(frame, dt)
+        # caller stand-in (local): buoyancy on v from T, written to DV_EXT, zero other changes
+        T, V, dV = r.f["T"], r.f["V"], r.f["DV_EXT"]
+        dV[:, 1:-1, :] = np.float32(0.5 * dt * 0.2) * (T[:, 1:, :] + T[:, :-1, :])
+        V += dV
+        st.accumulate(frame, dt)
+        log.append((st.stats["vel_reinit"], st.stats["scalar_reinit"], st.stats["halo_used"]))
+    owned = {}
+    for name in zslab.CUR + zslab.INIT + zslab.MAPS_BWD + zslab.MAPS_FWD:
+        dz = 1 if name in zslab.W_TYPE else 0
+        kb, ke = r.own(dz)
+        p0 = r.p0[name]
+        owned[name] = (kb, r.f[name][kb - p0:ke - p0].copy())
+    out_q.put((rank, owned, log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,blend", [(2, 1.0), (3, 0.5)])
+def test_gloo_slab_ranks_match_single_domain_oracle(oracle, world, blend):
+    ni, nj, nk, halo, frames = 16, 20, 36, 10, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ni, nj, nk, halo, frames, blend, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-domain oracle with the same forcing
+    h = 1.0 / ni
+    dt = 0.02
+    full = list(scenes.smoke_plume(ni, nj, nk, 1.0))
+    full[:3] = scenes.scale_to_cfl(*full[:3], h, dt, 1.5)
+    s = oracle.Solver(ni, nj, nk, h, blend)
+    s.set_initial(*full)
+    ref_log = []
+    for frame in range(frames):
+        s.advect(frame, dt)
+        adv = [a.copy() for a in s.cur]
+        dv = np.zeros_like(adv[1])
+        dv[:, 1:-1, :] = np.float32(0.5 * dt * 0.2) * (adv[4][:, 1:, :] + adv[4][:, :-1, :])
+        forced = [adv[0], adv[1] + dv, adv[2]]
+        final = forced + [adv[3], adv[4]]
+        # same change fields as the slab ranks form: d_ext = dv on v only, everything else zero
+        z = lambda a: oracle.padded(a.shape)
+        d_ext = [z(adv[0]), oracle.padded_copy(dv), z(adv[2])]
+        d_proj = [z(adv[0]), z(adv[1]), z(adv[2])]
+        for c in range(5):
+            s.cur[c][...] = final[c]
+        s.accumulate_changes(frame, dt, d_ext, d_proj, [z(adv[3]), z(adv[4])])
+        ref_log.append((s.stats["vel_reinit"], s.stats["scalar_reinit"]))
+    want = dict(zip(zslab.CUR, s.cur)); want.update(zip(zslab.INIT, s.init))
+    want.update(zip(zslab.MAPS_BWD, s.vel.bwd + s.sca.bwd)); want.update(zip(zslab.MAPS_FWD, s.vel.fwd + s.sca.fwd))
+    for rank, owned, log in results:
+        assert [(a, b) for a, b, _ in log] == ref_log
+        assert all(w <= halo for _, _, w in log)
+        for name, (kb, arr) in owned.items():
+            assert np.array_equal(arr, want[name][kb:kb + arr.shape[0]]), (rank, name)

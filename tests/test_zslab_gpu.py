@@ -1,0 +1,84 @@
+"""GPU tests of the z-slab path: N logical ranks on ONE device (LocalComm) must reproduce the
+single-GPU solver bit for bit -- owned planes of every field and map, the reinit sequence -- and,
+when the box has >= 2 GPUs, the same over NCCL with one process per GPU (tests/run_zslab_nccl.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gpufluidsimulation_b200 import scenes, zslab
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+CHECK = zslab.CUR + zslab.INIT + zslab.PREV + zslab.MAPS_BWD + zslab.MAPS_FWD + zslab.MAPS_BWDP
+
+
+@pytest.mark.parametrize("world,blend,L", [(2, 1.0, 1.0), (3, 0.5, 0.2), (4, 1.0, 1.0)])
+def test_logical_slabs_on_one_gpu_match_single_solver(cuda, world, blend, L):
+    from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
+    ni, nj, nk, halo, frames, dt = 32, 28, 48, 11, 6, 0.02
+    h = L / ni
+    u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, L)
+    u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
+    full = [u, v, w, rho, T]
+    single = BimocqAdvection3D(ni, nj, nk, h, blend)
+    single.set_initial(*full)
+    ranks = [zslab.CudaSlabRank(ni, nj, nk, h, blend, r, world, halo) for r in range(world)]
+    for r in ranks:
+        for name, a in zip(zslab.CUR, full):
+            _, p0, npl, _, _ = r.solver.field_info(name)
+            r.solver.upload(name, a[p0:p0 + npl])
+        r.solver.reset()
+    st = zslab.ZSlabStepper(ranks, zslab.LocalComm(world), blend)
+    for frame in range(frames):
+        single.advect(frame, dt)
+        st.advect(frame, dt)
+        single.apply_buoyancy(0.2, dt)
+        for r in ranks:
+            r.solver.apply_buoyancy(0.2, dt)
+        single.accumulate(frame, dt)
+        st.accumulate(frame, dt)
+        sst = single.stats()
+        assert (bool(sst["vel_reinit"]), bool(sst["scalar_reinit"])) == (st.stats["vel_reinit"], st.stats["scalar_reinit"])
+        assert st.stats["halo_used"] <= halo
+        for name in CHECK:
+            want = single.download(name)
+            dz = 1 if name in zslab.W_TYPE else 0
+            for r in ranks:
+                kb, ke = r.k0, r.k1 + (1 if dz and r.k1 == nk else 0)
+                got, p0 = r.field_with_origin(name)
+                assert np.array_equal(got[kb - p0:ke - p0].cpu().numpy(), want[kb:ke]), (frame, name, r.rank)
+    for r in ranks:
+        r.close()
+    single.close()
+
+
+def test_halo_overflow_raises(cuda):
+    ni, nj, nk = 24, 24, 32
+    h = 1.0 / ni
+    u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0)
+    u, v, w = scenes.scale_to_cfl(u, v, w, h, 0.02, 6.0)     # CFL 6 -> needs >= 9 halo planes
+    ranks = [zslab.CudaSlabRank(ni, nj, nk, h, 1.0, r, 2, 4) for r in range(2)]
+    for r in ranks:
+        for name, a in zip(zslab.CUR, (u, v, w, rho, T)):
+            _, p0, npl, _, _ = r.solver.field_info(name)
+            r.solver.upload(name, a[p0:p0 + npl])
+        r.solver.reset()
+    st = zslab.ZSlabStepper(ranks, zslab.LocalComm(2))
+    with pytest.raises(zslab.HaloTooNarrow):
+        st.advect(0, 0.02)
+    for r in ranks:
+        r.close()
+
+
+def test_nccl_two_processes(cuda):
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(HERE, "run_zslab_nccl.py")],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "ZSLAB_NCCL_OK" in out.stdout
