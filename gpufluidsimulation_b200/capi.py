@@ -69,6 +69,27 @@ FIELD.update({n: 64 + i for i, n in enumerate(
 
 N_TIMING_SLOTS = 16
 
+FIELD2_NAMES = [
+    "U", "V", "RHO", "T", "U_TEMP", "V_TEMP", "U_INIT", "V_INIT", "RHO_INIT", "T_INIT",
+    "U_ORIG", "V_ORIG", "RHO_ORIG", "T_ORIG", "DU", "DV", "DRHO", "DT", "DU_PREV", "DV_PREV", "DRHO_PREV", "DT_PREV",
+    "DU_EXT", "DV_EXT", "DRHO_EXT", "DT_EXT", "DU_PROJ", "DV_PROJ", "U_FORCED", "V_FORCED",
+    "FWD_X", "FWD_Y", "BWD_X", "BWD_Y", "BWDP_X", "BWDP_Y", "SFWD_X", "SFWD_Y", "SBWD_X", "SBWD_Y", "SBWDP_X", "SBWDP_Y",
+    "MAP_TMPX", "MAP_TMPY", "U_PRESAVE", "V_PRESAVE", "U_SAVE", "V_SAVE", "RHO_SAVE", "T_SAVE",
+    "U_SEMI", "V_SEMI", "RHO_SEMI", "T_SEMI",
+    "U_SCRATCH", "U_SCRATCH2", "V_SCRATCH", "V_SCRATCH2", "C_SCRATCH", "C_SCRATCH2",
+]
+FIELD2 = {n: i for i, n in enumerate(FIELD2_NAMES)}
+
+
+class Stats2D(C.Structure):
+    _fields_ = [("cfl", _f), ("max_vel_pre", _f), ("n_substeps", _I), ("max_vel", _f), ("vel_condition", _f),
+                ("scalar_condition", _f), ("vel_remap", _I), ("scalar_remap", _I), ("last_remesh", _I),
+                ("last_scalar_remesh", _I), ("total_remesh", _I), ("total_scalar_remesh", _I)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _PROTOS = {
     "bmq_last_error": (C.c_char_p, []),
     "bmq_clear_error": (_I, []),
@@ -104,6 +125,20 @@ _PROTOS = {
     "bmq3d_timing_slot_name": (C.c_char_p, [_I]),
     "bmq3d_advect_host": (_I, [_H, _I, _f] + [C.c_void_p] * 5),
     "bmq3d_accumulate_host": (_I, [_H, _I, _f] + [C.c_void_p] * 8),
+    "bmq2d_create": (_I, [_I, _I, _f, _f, C.POINTER(_H)]),
+    "bmq2d_destroy": (_I, [_H]),
+    "bmq2d_reset": (_I, [_H]),
+    "bmq2d_set_levelset": (_I, [_H, _I]),
+    "bmq2d_set_counters": (_I, [_H, _I, _I]),
+    "bmq2d_field_ptr": (_I, [_H, _I, C.POINTER(C.c_void_p), C.POINTER(_I), C.POINTER(_I)]),
+    "bmq2d_upload": (_I, [_H, _I, C.c_void_p]),
+    "bmq2d_download": (_I, [_H, _I, C.c_void_p]),
+    "bmq2d_advect": (_I, [_H, _I, _f]),
+    "bmq2d_accumulate": (_I, [_H, _I, _f]),
+    "bmq2d_get_stats": (_I, [_H, C.POINTER(Stats2D)]),
+    "bmq2d_advect_host": (_I, [_H, _I, _f] + [C.c_void_p] * 4),
+    "bmq2d_accumulate_host": (_I, [_H, _I, _f] + [C.c_void_p] * 6),
+    "bmq2d_kernel_launch_count": (C.c_ulonglong, [_H]),
     "bmq3d_stage_maxvel": (_I, [_H, C.POINTER(_f)]),
     "bmq3d_stage_set_cfl": (_I, [_H, _I, _f]),
     "bmq3d_stage_dmc_substep": (_I, [_H, _f]),

@@ -213,6 +213,59 @@ int bmq3d_stage_reinit(bmq3d_solver *s, int which, int phase);        /* phase 0
 enum { BMQ_F_U_ADV = 64, BMQ_F_V_ADV, BMQ_F_W_ADV, BMQ_F_RHO_ADV, BMQ_F_T_ADV,
        BMQ_F_U_ERR, BMQ_F_V_ERR, BMQ_F_W_ERR, BMQ_F_RHO_ERR, BMQ_F_T_ERR };
 
+/* ------------------------------------------------------------------ handle API (2D)
+ * The 2D reference (src/bimocq2D) is CPU code with no device seam; this API is the seam behind
+ * BimocqSolver2D::advanceBIMOCQ (bimocq2D/BimocqSolver2D.cpp:390-508), whose signature
+ * advance(float dt, int frame) (BimocqSolver2D.h:149) stays as it is.
+ * Fields are row-major a[i + ni*j] like Array2f (include/array2.h:93-103): u is (ni+1) x nj,
+ * v is ni x (nj+1), everything else ni x nj. */
+typedef struct bmq2d_solver bmq2d_solver;
+enum {
+    BMQ2_F_U = 0, BMQ2_F_V, BMQ2_F_RHO, BMQ2_F_T,                         /* BimocqSolver2D::u, v, rho, temperature */
+    BMQ2_F_U_TEMP, BMQ2_F_V_TEMP,                                         /* u_temp, v_temp (un-averaged velocity)  */
+    BMQ2_F_U_INIT, BMQ2_F_V_INIT, BMQ2_F_RHO_INIT, BMQ2_F_T_INIT,
+    BMQ2_F_U_ORIG, BMQ2_F_V_ORIG, BMQ2_F_RHO_ORIG, BMQ2_F_T_ORIG,         /* u_origin, v_origin, rho_orig, T_orig   */
+    BMQ2_F_DU, BMQ2_F_DV, BMQ2_F_DRHO, BMQ2_F_DT,
+    BMQ2_F_DU_PREV, BMQ2_F_DV_PREV, BMQ2_F_DRHO_PREV, BMQ2_F_DT_PREV,
+    BMQ2_F_DU_EXT, BMQ2_F_DV_EXT, BMQ2_F_DRHO_EXT, BMQ2_F_DT_EXT,         /* du_temp, dv_temp, drho_temp, dT_temp   */
+    BMQ2_F_DU_PROJ, BMQ2_F_DV_PROJ,
+    BMQ2_F_U_FORCED, BMQ2_F_V_FORCED,                                     /* velocity after the external forces     */
+    BMQ2_F_FWD_X, BMQ2_F_FWD_Y, BMQ2_F_BWD_X, BMQ2_F_BWD_Y, BMQ2_F_BWDP_X, BMQ2_F_BWDP_Y,
+    BMQ2_F_SFWD_X, BMQ2_F_SFWD_Y, BMQ2_F_SBWD_X, BMQ2_F_SBWD_Y, BMQ2_F_SBWDP_X, BMQ2_F_SBWDP_Y,
+    BMQ2_F_MAP_TMPX, BMQ2_F_MAP_TMPY,
+    BMQ2_F_U_PRESAVE, BMQ2_F_V_PRESAVE, BMQ2_F_U_SAVE, BMQ2_F_V_SAVE, BMQ2_F_RHO_SAVE, BMQ2_F_T_SAVE,
+    BMQ2_F_U_SEMI, BMQ2_F_V_SEMI, BMQ2_F_RHO_SEMI, BMQ2_F_T_SEMI,
+    BMQ2_F_U_SCRATCH, BMQ2_F_U_SCRATCH2, BMQ2_F_V_SCRATCH, BMQ2_F_V_SCRATCH2, BMQ2_F_C_SCRATCH, BMQ2_F_C_SCRATCH2,
+    BMQ2_F_COUNT
+};
+typedef struct bmq2d_stats {
+    float cfl;                /* _cfl = h / |maxVel()| used for the DMC sub-steps (BimocqSolver2D.cpp:53-56) */
+    float max_vel_pre;        /* maxVel() the CFL was taken from                                             */
+    int n_substeps;
+    float max_vel;            /* maxVel() of the post-projection velocity (:457)                             */
+    float vel_condition;      /* d_vel / (vel*dt), the printed "Velocity remapping condition" (:458)         */
+    float scalar_condition;
+    int vel_remap, scalar_remap;
+    int last_remesh, last_scalar_remesh, total_remesh, total_scalar_remesh;
+} bmq2d_stats;
+int bmq2d_create(int ni, int nj, float h, float blend_coeff, bmq2d_solver **out);
+int bmq2d_destroy(bmq2d_solver *s);
+int bmq2d_reset(bmq2d_solver *s);                                    /* constructor state (:156-270) */
+int bmq2d_set_levelset(bmq2d_solver *s, int on);                     /* advect_levelset (BimocqSolver2D.h:285) */
+int bmq2d_set_counters(bmq2d_solver *s, int lastremeshing, int rho_lastremeshing);
+int bmq2d_field_ptr(bmq2d_solver *s, int field_id, float **dev_ptr, int *fni, int *fnj);
+int bmq2d_upload(bmq2d_solver *s, int field_id, const float *host);
+int bmq2d_download(bmq2d_solver *s, int field_id, float *host);
+/* advanceBIMOCQ lines 394-445: CFL, map updates, semi-Lagrangian fields, advect + correct */
+int bmq2d_advect(bmq2d_solver *s, int frame, float dt);
+/* lines 449-507: on entry U_FORCED/V_FORCED = velocity after forces, U,V,RHO,T = after projection */
+int bmq2d_accumulate(bmq2d_solver *s, int frame, float dt);
+int bmq2d_get_stats(bmq2d_solver *s, bmq2d_stats *out);
+int bmq2d_advect_host(bmq2d_solver *s, int frame, float dt, float *u, float *v, float *rho, float *T);
+int bmq2d_accumulate_host(bmq2d_solver *s, int frame, float dt, const float *u_forced, const float *v_forced,
+                          float *u_final, float *v_final, const float *rho_final, const float *T_final);
+unsigned long long bmq2d_kernel_launch_count(bmq2d_solver *s);
+
 #ifdef __cplusplus
 }
 #endif
