@@ -302,6 +302,12 @@ def run_gpu(args):
         line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "note": "e2e through host buffers is measured at N=1"}
 
+    if world == 1 and rank == 0 and not args.no_2d:
+        try:
+            line["bimocq2d"] = measure_2d(torch)
+        except Exception as exc:   # secondary line: never lose the headline over it
+            line["bimocq2d"] = {"error": repr(exc)}
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
@@ -315,6 +321,49 @@ def run_gpu(args):
     solver.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_2d(torch, n=1024, steps=20, warm=5):
+    """BASELINE configs[1]: BiMocq2D 1024x1024 on one B200 (device-resident bmq2d_* path), vortex-in-a-box
+    flow with two scalar blobs; the caller stand-in between the phases is a device copy (zero forces)."""
+    from gpufluidsimulation_b200.solver2d import BimocqAdvection2D
+    L = 1.0
+    h = L / n
+    dt = 0.5 * h      # max |vel| = 2 -> CFL_frame ~ 1
+    xn = torch.arange(n + 1, dtype=torch.float64, device="cuda") / n
+    psi = 2.0 * L * (torch.sin(torch.pi * xn)[None, :] ** 2) * (torch.sin(torch.pi * xn)[:, None] ** 2) * L / torch.pi
+    u = ((psi[1:, :] - psi[:-1, :]) / h).float()
+    v = (-(psi[:, 1:] - psi[:, :-1]) / h).float()
+    xc = (torch.arange(n, dtype=torch.float64, device="cuda") + 0.5) / n
+    rho = torch.exp(-((xc[None, :] - 0.5) ** 2 + (xc[:, None] - 0.7) ** 2) / 0.12 ** 2).float()
+    T = torch.exp(-((xc[None, :] - 0.4) ** 2 + (xc[:, None] - 0.3) ** 2) / 0.1 ** 2).float()
+    s = BimocqAdvection2D(n, n, h, 1.0)
+    for name, a in (("U", u), ("V", v), ("U_INIT", u), ("V_INIT", v), ("RHO", rho), ("RHO_INIT", rho), ("T", T), ("T_INIT", T)):
+        s.field(name).copy_(a)
+
+    def step(frame):
+        s.advect(frame, dt)
+        s.field("U_FORCED").copy_(s.field("U")); s.field("V_FORCED").copy_(s.field("V"))
+        s.accumulate(frame, dt)
+
+    for f in range(warm):
+        step(f)
+    torch.cuda.synchronize()
+    l0 = s.launches()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for f in range(warm, warm + steps):
+        step(f)
+    e1.record(); e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    nsub = s.stats()["n_substeps"]
+    out = {"workload": f"BiMocq2D vortex-in-a-box {n}x{n}, velocity + 2 scalars", "ms_per_step": ms,
+           "cell_updates_per_s": n * n / (ms * 1e-3), "n_sub": nsub, "kernel_launches_per_step": (s.launches() - l0) / steps,
+           "alg_bytes_per_cell_update": 424 + 40 * nsub,
+           "hbm_roofline_frac": (424 + 40 * nsub) * n * n / (ms * 1e-3) / 1e9 / measured_peak()[0],
+           "note": "1 M cells x ~500 B = 0.5 GB/step: latency/launch bound, not HBM bound (BASELINE.md section 4)"}
+    s.close()
+    return out
 
 
 def measure_e2e(solver, torch, n, args, frame):
@@ -357,6 +406,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-2d", action="store_true", dest="no_2d")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

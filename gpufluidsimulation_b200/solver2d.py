@@ -41,6 +41,14 @@ class BimocqAdvection2D:
         check(self.lib.bmq2d_field_ptr(self._h, FIELD2[name], C.byref(ptr), C.byref(a), C.byref(b)), "bmq2d_field_ptr")
         return (b.value, a.value)
 
+    def field(self, name):
+        """Zero-copy torch view (nj, ni) of a device field (pointers rotate on remeshing: re-fetch)."""
+        import torch
+        from .solver3d import _DevView
+        ptr = C.c_void_p(); a = C.c_int(); b = C.c_int()
+        check(self.lib.bmq2d_field_ptr(self._h, FIELD2[name], C.byref(ptr), C.byref(a), C.byref(b)), "bmq2d_field_ptr")
+        return torch.as_tensor(_DevView(ptr.value, (b.value, a.value)), device="cuda")
+
     def upload(self, name, host):
         host = np.ascontiguousarray(host, dtype=np.float32)
         assert host.shape == self.shape(name), (name, host.shape, self.shape(name))
