@@ -16,7 +16,8 @@ class BimocqLibraryError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_PKG, "lib", "libbimocq_b200.so")
+    # BMQ_LIB: developer override for A/B-testing kernel variants (tools/); default is the in-tree build
+    return os.environ.get("BMQ_LIB") or os.path.join(_PKG, "lib", "libbimocq_b200.so")
 
 
 def header_path() -> str:

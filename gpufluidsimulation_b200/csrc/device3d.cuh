@@ -46,21 +46,33 @@ __device__ __forceinline__ float clampf(float a, float lo, float hi)
     return fminf(fmaxf(lo, a), hi);
 }
 
+// Two independent lerps in one instruction pair: sm_100a packed fp32 (FMUL2 + FFMA2).  Each
+// lane is the IEEE operation of lerp32, so results are bit-identical; only issue slots halve.
+__device__ __forceinline__ float2 lerp32x2(float2 a, float2 b, float2 f, float2 omf)
+{
+#ifdef BMQ_NO_PACKED_FP32
+    return make_float2(lerp32(a.x, b.x, f.x, omf.x), lerp32(a.y, b.y, f.y, omf.y));
+#else
+    return __ffma2_rn(omf, a, __fmul2_rn(f, b));
+#endif
+}
+
 // Trilinear sample of a dense x-fastest array; p points at node (x.i, y.i, z.i).
+// The x- and y-lerps of the two z-planes are paired ((z0,z1) lanes), so the nest costs
+// 2+2+... = 4 packed pairs + 1 scalar lerp instead of 7 scalar lerps; order x -> y -> z kept.
 __device__ __forceinline__ float tri8(const float *__restrict__ p, int sy, int sz, const Frac &x,
                                       const Frac &y, const Frac &z)
 {
-    float v000 = __ldg(p), v001 = __ldg(p + 1);
-    float v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
-    float v100 = __ldg(p + sz), v101 = __ldg(p + sz + 1);
-    float v110 = __ldg(p + sz + sy), v111 = __ldg(p + sz + sy + 1);
-    float a0 = lerp32(v000, v001, x.f, x.omf);
-    float a1 = lerp32(v010, v011, x.f, x.omf);
-    float a2 = lerp32(v100, v101, x.f, x.omf);
-    float a3 = lerp32(v110, v111, x.f, x.omf);
-    float b0 = lerp32(a0, a1, y.f, y.omf);
-    float b1 = lerp32(a2, a3, y.f, y.omf);
-    return lerp32(b0, b1, z.f, z.omf);
+    const float2 P0 = make_float2(__ldg(p), __ldg(p + sz));
+    const float2 P1 = make_float2(__ldg(p + 1), __ldg(p + sz + 1));
+    const float2 Q0 = make_float2(__ldg(p + sy), __ldg(p + sz + sy));
+    const float2 Q1 = make_float2(__ldg(p + sy + 1), __ldg(p + sz + sy + 1));
+    const float2 fx = make_float2(x.f, x.f), ox = make_float2(x.omf, x.omf);
+    const float2 fy = make_float2(y.f, y.f), oy = make_float2(y.omf, y.omf);
+    const float2 A = lerp32x2(P0, P1, fx, ox);   // (y0 row of z0, y0 row of z1)
+    const float2 B = lerp32x2(Q0, Q1, fx, ox);   // (y1 row of z0, y1 row of z1)
+    const float2 C = lerp32x2(A, B, fy, oy);     // (z0, z1)
+    return lerp32(C.x, C.y, z.f, z.omf);
 }
 
 // sample_buffer (GPU_kernel.cu:43-62) for a field of x-extent nx, y-extent ny whose origin is
@@ -104,6 +116,26 @@ __device__ __forceinline__ float3 get_velocity(const Vel3 &vel, const Grid3 &g, 
     {
         int sy = g.ni, sz = g.ni * g.nj;
         r.z = tri8(vel.w + (x0.i + sy * y0.i + sz * z5.i), sy, sz, x0, y0, z5);
+    }
+    return r;
+}
+
+// getVelocity at the grid node (i,j,k) when h is a power of two: every fraction is exactly 0
+// except 1/2 along the sampled component's own axis.
+__device__ __forceinline__ float3 velocity_at_node(const Vel3 &vel, const Grid3 &g, int i, int j, int k)
+{
+    float3 r;
+    {
+        const float *p = vel.u + (i + (g.ni + 1) * (j + g.nj * k));
+        r.x = lerp32(__ldg(p), __ldg(p + 1), 0.5f, 0.5f);
+    }
+    {
+        const float *p = vel.v + (i + g.ni * (j + (g.nj + 1) * k));
+        r.y = lerp32(__ldg(p), __ldg(p + g.ni), 0.5f, 0.5f);
+    }
+    {
+        const float *p = vel.w + (i + g.ni * (j + g.nj * k));
+        r.z = lerp32(__ldg(p), __ldg(p + g.ni * g.nj), 0.5f, 0.5f);
     }
     return r;
 }
@@ -317,36 +349,41 @@ __device__ __forceinline__ void window_samples(const float *__restrict__ p, int 
                                                const AxisW<P2, STAG == 3> &az, float (&out)[8], float &centre)
 {
     constexpr int NX = STAG == 1 ? 2 : 3, NY = STAG == 2 ? 2 : 3, NZ = STAG == 3 ? 2 : 3;
-    float Y[NZ][2][2];   // [z node][y sign][x sign]   (sign index 0 = plus, 1 = minus)
+    // every value is a pair over the x sign: .x = plus point, .y = minus point (packed fp32)
+    const float2 fx = make_float2(ax.fp, ax.fm), ox = make_float2(ax.op, ax.om);
+    const float2 fym = make_float2(ay.fm, ay.fm), oym = make_float2(ay.om, ay.om);
+    const float2 fyp = make_float2(ay.fp, ay.fp), oyp = make_float2(ay.op, ay.op);
+    const float2 fzm = make_float2(az.fm, az.fm), ozm = make_float2(az.om, az.om);
+    const float2 fzp = make_float2(az.fp, az.fp), ozp = make_float2(az.op, az.op);
+    float2 Y[NZ][2];     // [z node][y sign] (0 = plus, 1 = minus)
     float cyz[NZ];       // centre-line values per z node (P2 only)
 #pragma unroll
     for (int z = 0; z < NZ; ++z) {
-        float X[NY][2];
+        float2 X[NY];
         float xc[NY];
 #pragma unroll
         for (int y = 0; y < NY; ++y) {
             const float *r = p + y * sy + z * sz;
             const float n0 = __ldg(r), n1 = __ldg(r + 1);
             const float n2 = NX == 3 ? __ldg(r + 2) : 0.f;
-            X[y][1] = lerp32(n0, n1, ax.fm, ax.om);
-            X[y][0] = NX == 3 ? lerp32(n1, n2, ax.fp, ax.op) : lerp32(n0, n1, ax.fp, ax.op);
+            // plus point: cells (n1,n2) unstaggered / (n0,n1) staggered; minus point: (n0,n1)
+            X[y] = NX == 3 ? lerp32x2(make_float2(n1, n0), make_float2(n2, n1), fx, ox)
+                           : lerp32x2(make_float2(n0, n0), make_float2(n1, n1), fx, ox);
             if (P2) xc[y] = NX == 3 ? n1 : lerp32(n0, n1, 0.5f, 0.5f);
         }
-#pragma unroll
-        for (int sx = 0; sx < 2; ++sx) {
-            Y[z][1][sx] = lerp32(X[0][sx], X[1][sx], ay.fm, ay.om);
-            Y[z][0][sx] = NY == 3 ? lerp32(X[1][sx], X[2][sx], ay.fp, ay.op) : lerp32(X[0][sx], X[1][sx], ay.fp, ay.op);
-        }
+        Y[z][1] = lerp32x2(X[0], X[1], fym, oym);
+        Y[z][0] = NY == 3 ? lerp32x2(X[1], X[2], fyp, oyp) : lerp32x2(X[0], X[1], fyp, oyp);
         if (P2) cyz[z] = NY == 3 ? xc[1] : lerp32(xc[0], xc[1], 0.5f, 0.5f);
     }
 #pragma unroll
-    for (int sx = 0; sx < 2; ++sx)
-#pragma unroll
-        for (int sy_ = 0; sy_ < 2; ++sy_) {
-            out[sx * 4 + sy_ * 2 + 1] = lerp32(Y[0][sy_][sx], Y[1][sy_][sx], az.fm, az.om);
-            out[sx * 4 + sy_ * 2 + 0] =
-                NZ == 3 ? lerp32(Y[1][sy_][sx], Y[2][sy_][sx], az.fp, az.op) : lerp32(Y[0][sy_][sx], Y[1][sy_][sx], az.fp, az.op);
-        }
+    for (int sy_ = 0; sy_ < 2; ++sy_) {
+        const float2 zm = lerp32x2(Y[0][sy_], Y[1][sy_], fzm, ozm);
+        const float2 zp = NZ == 3 ? lerp32x2(Y[1][sy_], Y[2][sy_], fzp, ozp) : lerp32x2(Y[0][sy_], Y[1][sy_], fzp, ozp);
+        out[0 * 4 + sy_ * 2 + 1] = zm.x;   // x plus,  z minus
+        out[1 * 4 + sy_ * 2 + 1] = zm.y;   // x minus, z minus
+        out[0 * 4 + sy_ * 2 + 0] = zp.x;
+        out[1 * 4 + sy_ * 2 + 0] = zp.y;
+    }
     if (P2) centre = NZ == 3 ? cyz[1] : lerp32(cyz[0], cyz[1], 0.5f, 0.5f);
 }
 

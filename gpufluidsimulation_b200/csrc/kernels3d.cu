@@ -86,12 +86,26 @@ k_dmc(Grid3 g, int kbeg, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float 
     const int idx = i + g.ni * (j + g.nj * k);
     const float h = g.h;
     const float px = h * (float)i, py = h * (float)j, pz = h * (float)k;
-    // bit-exact reference arithmetic for the two velocity samples (see lerp_ref in device3d.cuh)
-    float3 v0 = P2 ? get_velocity<true>(vel, g, px, py, pz) : get_velocity_ref(vel, g, px, py, pz);
-    const float tx = v0.x > 0.f ? px - h : px + h;
-    const float ty = v0.y > 0.f ? py - h : py + h;
-    const float tz = v0.z > 0.f ? pz - h : pz + h;
-    float3 v1 = P2 ? get_velocity<true>(vel, g, tx, ty, tz) : get_velocity_ref(vel, g, tx, ty, tz);
+    // Two velocity samples.  General h: bit-exact reference arithmetic (lerp_ref in device3d.cuh).
+    // Power-of-two h: both points are grid nodes, where the staggered component has fraction 1/2
+    // and the other two axes fraction 0, so each component is the mean of two faces (2 loads
+    // instead of 8; the dropped terms have weight exactly 0).
+    float3 v0, v1;
+    float tx, ty, tz;
+    if (P2) {
+        v0 = velocity_at_node(vel, g, i, j, k);
+        const int it = v0.x > 0.f ? i - 1 : i + 1, jt = v0.y > 0.f ? j - 1 : j + 1, kt = v0.z > 0.f ? k - 1 : k + 1;
+        tx = v0.x > 0.f ? px - h : px + h;
+        ty = v0.y > 0.f ? py - h : py + h;
+        tz = v0.z > 0.f ? pz - h : pz + h;
+        v1 = velocity_at_node(vel, g, it, jt, kt);
+    } else {
+        v0 = get_velocity_ref(vel, g, px, py, pz);
+        tx = v0.x > 0.f ? px - h : px + h;
+        ty = v0.y > 0.f ? py - h : py + h;
+        tz = v0.z > 0.f ? pz - h : pz + h;
+        v1 = get_velocity_ref(vel, g, tx, ty, tz);
+    }
     const float ax = (v0.x - v1.x) / (px - tx);
     const float ay = (v0.y - v1.y) / (py - ty);
     const float az = (v0.z - v1.z) / (pz - tz);
@@ -263,6 +277,9 @@ k_apply_clamp(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, Fie
 // Same arithmetic as k_advect / k_error / k_cumulate / k_apply_clamp with is_point == false, but
 // the map samples of the 8 sub-cell points come from one node window per map component
 // (quad_gather_win in device3d.cuh).  STAG: 0 centred, 1/2/3 = u/v/w faces (compile time).
+#ifndef BMQ_WIN_MINBLOCKS
+#define BMQ_WIN_MINBLOCKS 5   // <= 51 registers: 5 CTAs/SM hide the dependent map->field gather latency (A/B in profiles/r1_variants.txt)
+#endif
 #define BMQ_STAG_SETUP                                                                             \
     constexpr int DX = STAG == 1, DY = STAG == 2, DZ = STAG == 3;                                  \
     const int fi = g.ni + DX, fj = g.nj + DY, fk = g.nk + DZ;                                      \
@@ -274,7 +291,7 @@ k_apply_clamp(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, Fie
     const int idx = i + fi * (j + fj * k);
 
 template <bool P2, int STAG, int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
 k_advect_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
 {
     BMQ_STAG_SETUP
@@ -289,7 +306,7 @@ k_advect_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 ch
 }
 
 template <bool P2, int STAG, int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
 k_error_win(Grid3 g, int kbeg, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
 {
     BMQ_STAG_SETUP
@@ -304,7 +321,7 @@ k_error_win(Grid3 g, int kbeg, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO
 }
 
 template <bool P2, int STAG, int NF, int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
 k_cumulate_win(Grid3 g, int kbeg, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change, Coeffs<NCH> coeff, Map3 map)
 {
     BMQ_STAG_SETUP
@@ -329,7 +346,7 @@ k_cumulate_win(Grid3 g, int kbeg, FieldSetRW<NF> target, FieldSetRO<NF * NCH> ch
 }
 
 template <bool P2, int STAG, int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
 k_apply_clamp_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> fadv, FieldSetRO<NF> e0, Map3 chi)
 {
     BMQ_STAG_SETUP
@@ -456,10 +473,12 @@ k_estimate(Grid3 g, int kbeg, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NM
 #pragma unroll
         for (int m = 0; m < NMAP; ++m) {
             Map3 B{bwd.x[m], bwd.y[m], bwd.z[m]}, F{fwd.x[m], fwd.y[m], fwd.z[m]};
-            float3 b = sample_map<P2>(B, g, px, py, pz);
+            // the first sample of each round trip is taken AT the cell centre, a map node: with
+            // power-of-two h its fractions are exactly 0 and the sample is the node value
+            float3 b = P2 ? make_float3(__ldg(B.x + idx), __ldg(B.y + idx), __ldg(B.z + idx)) : sample_map<P2>(B, g, px, py, pz);
             float3 f = sample_map<P2>(F, g, b.x, b.y, b.z);
             const float dbf = (px - f.x) * (px - f.x) + (py - f.y) * (py - f.y) + (pz - f.z) * (pz - f.z);
-            float3 f2 = sample_map<P2>(F, g, px, py, pz);
+            float3 f2 = P2 ? make_float3(__ldg(F.x + idx), __ldg(F.y + idx), __ldg(F.z + idx)) : sample_map<P2>(F, g, px, py, pz);
             float3 b2 = sample_map<P2>(B, g, f2.x, f2.y, f2.z);
             const float dfb = (px - b2.x) * (px - b2.x) + (py - b2.y) * (py - b2.y) + (pz - b2.z) * (pz - b2.z);
             const float d = fmaxf(dbf, dfb);
