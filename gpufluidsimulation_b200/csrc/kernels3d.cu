@@ -35,24 +35,32 @@ Grid3 make_grid(int ni, int nj, int nk, float h)
     return g;
 }
 
-static inline dim3 block3() { return dim3(32, 8, 1); }
+// CTA shape (32, BMQ_BY, BMQ_BZ), 256 threads.  A CTA that spans several z-planes shares the
+// k-1/k/k+1 planes of the map windows and of the near-identity field gathers in L1.
+#ifndef BMQ_BY
+#define BMQ_BY 8
+#endif
+#ifndef BMQ_BZ
+#define BMQ_BZ 1
+#endif
+static inline dim3 block3() { return dim3(32, BMQ_BY, BMQ_BZ); }
 static inline dim3 grid3(int fi, int fj, KRange r)
 {
-    return dim3((fi + 31) / 32, (fj + 7) / 8, r.kend - r.kbeg);
+    return dim3((fi + 31) / 32, (fj + BMQ_BY - 1) / BMQ_BY, (r.kend - r.kbeg + BMQ_BZ - 1) / BMQ_BZ);
 }
 
 #define BMQ_IJK(fi, fj)                                          \
     const int i = blockIdx.x * 32 + threadIdx.x;                 \
-    const int j = blockIdx.y * 8 + threadIdx.y;                  \
-    const int k = kbeg + blockIdx.z;                             \
-    if (i >= (fi) || j >= (fj)) return;
+    const int j = blockIdx.y * BMQ_BY + threadIdx.y;             \
+    const int k = kbeg + blockIdx.z * BMQ_BZ + threadIdx.z;      \
+    if (i >= (fi) || j >= (fj) || k >= kend_) return;
 
 // ------------------------------------------------------------------ forward map (a4)
 // forward_kernel, GPU_kernel.cu:127-144: psi <- trace(psi, +dt) in place, NMAP mappers at once
 // (each mapper's particle is independent; tracing two per thread doubles the loads in flight).
 template <bool P2, int NMAP>
 __global__ void __launch_bounds__(256)
-k_forward(Grid3 g, int kbeg, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
+k_forward(Grid3 g, int kbeg, int kend_, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
 {
     BMQ_IJK(g.ni, g.nj)
     if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
@@ -79,7 +87,7 @@ __device__ __forceinline__ float dmc_axis(float p, float v, float a, float s)
 
 template <bool P2, int NMAP>
 __global__ void __launch_bounds__(256)
-k_dmc(Grid3 g, int kbeg, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
+k_dmc(Grid3 g, int kbeg, int kend_, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
 {
     BMQ_IJK(g.ni, g.nj)
     if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
@@ -127,7 +135,7 @@ k_dmc(Grid3 g, int kbeg, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float 
 // semilag_kernel, GPU_kernel.cu:206-233; NF co-located fields share one back-trace.
 template <bool P2, int NF>
 __global__ void __launch_bounds__(256)
-k_semilag(Grid3 g, int kbeg, Vel3 vel, Stag st, FieldSetRW<NF> out, FieldSetRO<NF> src, float cfldt, float dt)
+k_semilag(Grid3 g, int kbeg, int kend_, Vel3 vel, Stag st, FieldSetRW<NF> out, FieldSetRO<NF> src, float cfldt, float dt)
 {
     const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
     BMQ_IJK(fi, fj)
@@ -146,7 +154,7 @@ k_semilag(Grid3 g, int kbeg, Vel3 vel, Stag st, FieldSetRW<NF> out, FieldSetRO<N
 // advect_kernel, GPU_kernel.cu:312-374: f = 1/2 * sum_8 1/8 f0(clamp(chi(x+d))) + 1/2 f0(clamp(chi(x)))
 template <bool P2, int NF>
 __global__ void __launch_bounds__(256)
-k_advect(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
+k_advect(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
 {
     const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
     BMQ_IJK(fi, fj)
@@ -168,7 +176,7 @@ k_advect(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, FieldSet
 // compensate_kernel, GPU_kernel.cu:438-499: e0 = quad9[f(clamp0(psi(x+d)))] - f_init
 template <bool P2, int NF>
 __global__ void __launch_bounds__(256)
-k_error(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
+k_error(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
 {
     const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
     BMQ_IJK(fi, fj)
@@ -193,7 +201,7 @@ k_error(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> e0, FieldSetRO
 // consecutive launches give.
 template <bool P2, int NF, int NCH>
 __global__ void __launch_bounds__(256)
-k_cumulate(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change,
+k_cumulate(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change,
            Coeffs<NCH> coeff, Map3 map)
 {
     const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
@@ -230,7 +238,7 @@ k_cumulate(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> target, Fie
 // out may be a different buffer than f_adv and no device-to-device copy is needed.
 template <bool P2, int NF>
 __global__ void __launch_bounds__(256)
-k_apply_clamp(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, FieldSetRO<NF> fadv,
+k_apply_clamp(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<NF> out, FieldSetRO<NF> fadv,
               FieldSetRO<NF> e0, Map3 chi)
 {
     const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
@@ -292,7 +300,7 @@ k_apply_clamp(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> out, Fie
 
 template <bool P2, int STAG, int NF>
 __global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
-k_advect_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
+k_advect_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
 {
     BMQ_STAG_SETUP
     if (!(2 + DX < i && i < fi - 3 && 2 + DY < j && j < fj - 3 && 2 + DZ < k && k < fk - 3)) return;
@@ -307,7 +315,7 @@ k_advect_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 ch
 
 template <bool P2, int STAG, int NF>
 __global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
-k_error_win(Grid3 g, int kbeg, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
+k_error_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
 {
     BMQ_STAG_SETUP
     if (!(1 + DX < i && i < fi - 2 && 1 + DY < j && j < fj - 2 && 1 + DZ < k && k < fk - 2)) return;
@@ -322,7 +330,7 @@ k_error_win(Grid3 g, int kbeg, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO
 
 template <bool P2, int STAG, int NF, int NCH>
 __global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
-k_cumulate_win(Grid3 g, int kbeg, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change, Coeffs<NCH> coeff, Map3 map)
+k_cumulate_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change, Coeffs<NCH> coeff, Map3 map)
 {
     BMQ_STAG_SETUP
     if (!(1 + DX < i && i < fi - 2 && 1 + DY < j && j < fj - 2 && 1 + DZ < k && k < fk - 2)) return;
@@ -347,7 +355,7 @@ k_cumulate_win(Grid3 g, int kbeg, FieldSetRW<NF> target, FieldSetRO<NF * NCH> ch
 
 template <bool P2, int STAG, int NF>
 __global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
-k_apply_clamp_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> fadv, FieldSetRO<NF> e0, Map3 chi)
+k_apply_clamp_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> fadv, FieldSetRO<NF> e0, Map3 chi)
 {
     BMQ_STAG_SETUP
     float r[NF];
@@ -386,7 +394,7 @@ k_apply_clamp_win(Grid3 g, int kbeg, FieldSetRW<NF> out, FieldSetRO<NF> fadv, Fi
 
 // clampExtrema_kernel alone (legacy gpu_compensate_* keeps the reference's buffer contract)
 __global__ void __launch_bounds__(256)
-k_clamp_extrema(int fi, int fj, int fk, int kbeg, const float *__restrict__ before, float *after)
+k_clamp_extrema(int fi, int fj, int fk, int kbeg, int kend_, const float *__restrict__ before, float *after)
 {
     BMQ_IJK(fi, fj)
     if (!(i > 0 && i < fi - 1 && j > 0 && j < fj - 1 && k > 0 && k < fk - 1)) return;
@@ -409,7 +417,7 @@ k_clamp_extrema(int fi, int fj, int fk, int kbeg, const float *__restrict__ befo
 // doubleAdvect_kernel, GPU_kernel.cu:236-310
 template <bool P2, int NF>
 __global__ void __launch_bounds__(256)
-k_double_advect(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> field, FieldSetRO<NF> prev,
+k_double_advect(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<NF> field, FieldSetRO<NF> prev,
                 Map3 chi, Map3 chip, float blend)
 {
     const int fi = g.ni + st.dx, fj = g.nj + st.dy, fk = g.nk + st.dz;
@@ -456,16 +464,16 @@ k_double_advect(Grid3 g, int kbeg, Stag st, bool is_point, FieldSetRW<NF> field,
 // atomicMax per block.  Also reduces max |map_z - z| (in world units) for halo sizing.
 template <bool P2, int NMAP>
 __global__ void __launch_bounds__(256)
-k_estimate(Grid3 g, int kbeg, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
+k_estimate(Grid3 g, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
            const signed char *__restrict__ boundary)
 {
     const int i = blockIdx.x * 32 + threadIdx.x;
-    const int j = blockIdx.y * 8 + threadIdx.y;
-    const int k = kbeg + blockIdx.z;
+    const int j = blockIdx.y * BMQ_BY + threadIdx.y;
+    const int k = kbeg + blockIdx.z * BMQ_BZ + threadIdx.z;
     float d2[NMAP], dispz = 0.f;
 #pragma unroll
     for (int m = 0; m < NMAP; ++m) d2[m] = 0.f;
-    const bool inside = i < g.ni && j < g.nj;
+    const bool inside = i < g.ni && j < g.nj && k < kend_;
     if (inside && i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2) {
         const int idx = i + g.ni * (j + g.nj * k);
         const float px = g.h * (float)i, py = g.h * (float)j, pz = g.h * (float)k;
@@ -540,7 +548,7 @@ k_add_field(float *out, const float *__restrict__ a, const float *__restrict__ b
 }
 
 // identity maps x = i*h (Mapping.cpp:310-324) for up to two mappers x (psi, chi)
-__global__ void __launch_bounds__(256) k_identity(Grid3 g, int kbeg, IdentityOut o)
+__global__ void __launch_bounds__(256) k_identity(Grid3 g, int kbeg, int kend_, IdentityOut o)
 {
     BMQ_IJK(g.ni, g.nj)
     const int idx = i + g.ni * (j + g.nj * k);
@@ -562,13 +570,13 @@ cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float
     dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
     if (nmap == 1) {
         MapSetRW<1> m; m.x[0] = maps[0][0]; m.y[0] = maps[0][1]; m.z[0] = maps[0][2];
-        DISPATCH_P2(g, (k_forward<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)),
-                    (k_forward<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)));
+        DISPATCH_P2(g, (k_forward<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)),
+                    (k_forward<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)));
     } else {
         MapSetRW<2> m;
         for (int q = 0; q < 2; ++q) { m.x[q] = maps[q][0]; m.y[q] = maps[q][1]; m.z[q] = maps[q][2]; }
-        DISPATCH_P2(g, (k_forward<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)),
-                    (k_forward<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, m, cfldt, dt)));
+        DISPATCH_P2(g, (k_forward<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)),
+                    (k_forward<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)));
     }
     count_launch();
     return cudaGetLastError();
@@ -585,16 +593,16 @@ cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u,
         MapSetRO<1> a; MapSetRW<1> b;
         a.x[0] = in[0][0]; a.y[0] = in[0][1]; a.z[0] = in[0][2];
         b.x[0] = out[0][0]; b.y[0] = out[0][1]; b.z[0] = out[0][2];
-        DISPATCH_P2(g, (k_dmc<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)),
-                    (k_dmc<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)));
+        DISPATCH_P2(g, (k_dmc<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)),
+                    (k_dmc<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)));
     } else {
         MapSetRO<2> a; MapSetRW<2> b;
         for (int q = 0; q < 2; ++q) {
             a.x[q] = in[q][0]; a.y[q] = in[q][1]; a.z[q] = in[q][2];
             b.x[q] = out[q][0]; b.y[q] = out[q][1]; b.z[q] = out[q][2];
         }
-        DISPATCH_P2(g, (k_dmc<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)),
-                    (k_dmc<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, a, b, substep)));
+        DISPATCH_P2(g, (k_dmc<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)),
+                    (k_dmc<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)));
     }
     count_launch();
     return cudaGetLastError();
@@ -626,11 +634,11 @@ cudaError_t launch_semilag(cudaStream_t s, const Grid3 &g, KRange r, Stag st, co
     Vel3 vel{u, v, w};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (nf == 1)
-        DISPATCH_P2(g, (k_semilag<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<1>(out), ro<1>(src), cfldt, dt)),
-                    (k_semilag<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<1>(out), ro<1>(src), cfldt, dt)));
+        DISPATCH_P2(g, (k_semilag<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, st, rw<1>(out), ro<1>(src), cfldt, dt)),
+                    (k_semilag<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, st, rw<1>(out), ro<1>(src), cfldt, dt)));
     else
-        DISPATCH_P2(g, (k_semilag<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<2>(out), ro<2>(src), cfldt, dt)),
-                    (k_semilag<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, vel, st, rw<2>(out), ro<2>(src), cfldt, dt)));
+        DISPATCH_P2(g, (k_semilag<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, st, rw<2>(out), ro<2>(src), cfldt, dt)),
+                    (k_semilag<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, st, rw<2>(out), ro<2>(src), cfldt, dt)));
     count_launch();
     return cudaGetLastError();
 }
@@ -638,8 +646,8 @@ cudaError_t launch_semilag(cudaStream_t s, const Grid3 &g, KRange r, Stag st, co
 static void k_dispatch_centred2_advect(cudaStream_t s, const Grid3 &g, KRange r, dim3 gr, dim3 bl, float *const *out,
                                        const float *const *init, Map3 m)
 {
-    if (is_pow2_h(g)) k_advect_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(init), m);
-    else k_advect_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(init), m);
+    if (is_pow2_h(g)) k_advect_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
+    else k_advect_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
 }
 
 cudaError_t launch_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
@@ -649,17 +657,17 @@ cudaError_t launch_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, boo
     Map3 m{chi[0], chi[1], chi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
-        if (nf == 1) DISPATCH_STAG_P2(g, st, k_advect_win, 1, g, r.kbeg, rw<1>(out), ro<1>(init), m);
+        if (nf == 1) DISPATCH_STAG_P2(g, st, k_advect_win, 1, g, r.kbeg, r.kend, rw<1>(out), ro<1>(init), m);
         else k_dispatch_centred2_advect(s, g, r, gr, bl, out, init, m);
         count_launch();
         return cudaGetLastError();
     }
     if (nf == 1)
-        DISPATCH_P2(g, (k_advect<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(init), m)),
-                    (k_advect<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(init), m)));
+        DISPATCH_P2(g, (k_advect<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(out), ro<1>(init), m)),
+                    (k_advect<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(out), ro<1>(init), m)));
     else
-        DISPATCH_P2(g, (k_advect<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(init), m)),
-                    (k_advect<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(init), m)));
+        DISPATCH_P2(g, (k_advect<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(out), ro<2>(init), m)),
+                    (k_advect<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(out), ro<2>(init), m)));
     count_launch();
     return cudaGetLastError();
 }
@@ -672,18 +680,18 @@ cudaError_t launch_error(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool
     Map3 m{psi[0], psi[1], psi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
-        if (nf == 1) DISPATCH_STAG_P2(g, st, k_error_win, 1, g, r.kbeg, rw<1>(e0), ro<1>(src), ro<1>(init), m);
-        else if (is_pow2_h(g)) k_error_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(e0), ro<2>(src), ro<2>(init), m);
-        else k_error_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(e0), ro<2>(src), ro<2>(init), m);
+        if (nf == 1) DISPATCH_STAG_P2(g, st, k_error_win, 1, g, r.kbeg, r.kend, rw<1>(e0), ro<1>(src), ro<1>(init), m);
+        else if (is_pow2_h(g)) k_error_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
+        else k_error_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
         count_launch();
         return cudaGetLastError();
     }
     if (nf == 1)
-        DISPATCH_P2(g, (k_error<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)),
-                    (k_error<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)));
+        DISPATCH_P2(g, (k_error<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)),
+                    (k_error<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(e0), ro<1>(src), ro<1>(init), m)));
     else
-        DISPATCH_P2(g, (k_error<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(e0), ro<2>(src), ro<2>(init), m)),
-                    (k_error<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(e0), ro<2>(src), ro<2>(init), m)));
+        DISPATCH_P2(g, (k_error<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(e0), ro<2>(src), ro<2>(init), m)),
+                    (k_error<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(e0), ro<2>(src), ro<2>(init), m)));
     count_launch();
     return cudaGetLastError();
 }
@@ -698,14 +706,14 @@ cudaError_t launch_cumulate(cudaStream_t s, const Grid3 &g, KRange r, Stag st, b
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1 && nch == 1) {
             Coeffs<1> c; c.c[0] = coeff[0];
-            DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 1, g, r.kbeg, rw<1>(target), ro<1>(change), c, m);
+            DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 1, g, r.kbeg, r.kend, rw<1>(target), ro<1>(change), c, m);
         } else if (nf == 1 && nch == 2) {
             Coeffs<2> c; c.c[0] = coeff[0]; c.c[1] = coeff[1];
-            DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 2, g, r.kbeg, rw<1>(target), ro<2>(change), c, m);
+            DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 2, g, r.kbeg, r.kend, rw<1>(target), ro<2>(change), c, m);
         } else if (nf == 2 && nch == 1) {
             Coeffs<1> c; c.c[0] = coeff[0];
-            if (is_pow2_h(g)) k_cumulate_win<true, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(target), ro<2>(change), c, m);
-            else k_cumulate_win<false, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(target), ro<2>(change), c, m);
+            if (is_pow2_h(g)) k_cumulate_win<true, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
+            else k_cumulate_win<false, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
         } else return cudaErrorInvalidValue;
         count_launch();
         return cudaGetLastError();
@@ -714,8 +722,8 @@ cudaError_t launch_cumulate(cudaStream_t s, const Grid3 &g, KRange r, Stag st, b
     {                                                                                                  \
         Coeffs<NCH> c;                                                                                 \
         for (int q = 0; q < NCH; ++q) c.c[q] = coeff[q];                                               \
-        DISPATCH_P2(g, (k_cumulate<true, NF, NCH><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<NF>(target), ro<NF * NCH>(change), c, m)), \
-                    (k_cumulate<false, NF, NCH><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<NF>(target), ro<NF * NCH>(change), c, m))); \
+        DISPATCH_P2(g, (k_cumulate<true, NF, NCH><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<NF>(target), ro<NF * NCH>(change), c, m)), \
+                    (k_cumulate<false, NF, NCH><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<NF>(target), ro<NF * NCH>(change), c, m))); \
     }
     if (nf == 1 && nch == 1) CUM(1, 1)
     else if (nf == 1 && nch == 2) CUM(1, 2)
@@ -734,18 +742,18 @@ cudaError_t launch_apply_clamp(cudaStream_t s, const Grid3 &g, KRange r, Stag st
     Map3 m{chi[0], chi[1], chi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
-        if (nf == 1) DISPATCH_STAG_P2(g, st, k_apply_clamp_win, 1, g, r.kbeg, rw<1>(out), ro<1>(fadv), ro<1>(e0), m);
-        else if (is_pow2_h(g)) k_apply_clamp_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
-        else k_apply_clamp_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
+        if (nf == 1) DISPATCH_STAG_P2(g, st, k_apply_clamp_win, 1, g, r.kbeg, r.kend, rw<1>(out), ro<1>(fadv), ro<1>(e0), m);
+        else if (is_pow2_h(g)) k_apply_clamp_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
+        else k_apply_clamp_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
         count_launch();
         return cudaGetLastError();
     }
     if (nf == 1)
-        DISPATCH_P2(g, (k_apply_clamp<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)),
-                    (k_apply_clamp<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)));
+        DISPATCH_P2(g, (k_apply_clamp<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)),
+                    (k_apply_clamp<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(out), ro<1>(fadv), ro<1>(e0), m)));
     else
-        DISPATCH_P2(g, (k_apply_clamp<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(fadv), ro<2>(e0), m)),
-                    (k_apply_clamp<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(out), ro<2>(fadv), ro<2>(e0), m)));
+        DISPATCH_P2(g, (k_apply_clamp<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(out), ro<2>(fadv), ro<2>(e0), m)),
+                    (k_apply_clamp<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(out), ro<2>(fadv), ro<2>(e0), m)));
     count_launch();
     return cudaGetLastError();
 }
@@ -754,7 +762,7 @@ cudaError_t launch_clamp_extrema(cudaStream_t s, int fi, int fj, int fk, KRange 
                                  float *after)
 {
     if (r.kend <= r.kbeg) return cudaSuccess;
-    k_clamp_extrema<<<grid3(fi, fj, r), block3(), 0, s>>>(fi, fj, fk, r.kbeg, before, after);
+    k_clamp_extrema<<<grid3(fi, fj, r), block3(), 0, s>>>(fi, fj, fk, r.kbeg, r.kend, before, after);
     count_launch();
     return cudaGetLastError();
 }
@@ -767,11 +775,11 @@ cudaError_t launch_double_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag 
     Map3 m{chi[0], chi[1], chi[2]}, mp{chip[0], chip[1], chip[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (nf == 1)
-        DISPATCH_P2(g, (k_double_advect<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(field), ro<1>(prev), m, mp, blend)),
-                    (k_double_advect<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<1>(field), ro<1>(prev), m, mp, blend)));
+        DISPATCH_P2(g, (k_double_advect<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(field), ro<1>(prev), m, mp, blend)),
+                    (k_double_advect<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<1>(field), ro<1>(prev), m, mp, blend)));
     else
-        DISPATCH_P2(g, (k_double_advect<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(field), ro<2>(prev), m, mp, blend)),
-                    (k_double_advect<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, st, is_point, rw<2>(field), ro<2>(prev), m, mp, blend)));
+        DISPATCH_P2(g, (k_double_advect<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(field), ro<2>(prev), m, mp, blend)),
+                    (k_double_advect<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, st, is_point, rw<2>(field), ro<2>(prev), m, mp, blend)));
     count_launch();
     return cudaGetLastError();
 }
@@ -787,8 +795,8 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
         b.x[0] = bwd[0][0]; b.y[0] = bwd[0][1]; b.z[0] = bwd[0][2];
         f.x[0] = fwd[0][0]; f.y[0] = fwd[0][1]; f.z[0] = fwd[0][2];
         o.dist[0] = dist ? dist[0] : nullptr; o.d2max[0] = d2max ? d2max[0] : nullptr; o.dispz = dispz;
-        DISPATCH_P2(g, (k_estimate<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)),
-                    (k_estimate<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)));
+        DISPATCH_P2(g, (k_estimate<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)),
+                    (k_estimate<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)));
     } else {
         MapSetRO<2> b, f; DistOut<2> o;
         for (int q = 0; q < 2; ++q) {
@@ -797,8 +805,8 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
             o.dist[q] = dist ? dist[q] : nullptr; o.d2max[q] = d2max ? d2max[q] : nullptr;
         }
         o.dispz = dispz;
-        DISPATCH_P2(g, (k_estimate<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)),
-                    (k_estimate<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, b, f, o, boundary)));
+        DISPATCH_P2(g, (k_estimate<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)),
+                    (k_estimate<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)));
     }
     count_launch();
     return cudaGetLastError();
@@ -848,7 +856,7 @@ cudaError_t launch_identity(cudaStream_t s, const Grid3 &g, KRange r, int nsets,
         o.y[m] = m < nsets ? sets[m][1] : nullptr;
         o.z[m] = m < nsets ? sets[m][2] : nullptr;
     }
-    k_identity<<<grid3(g.ni, g.nj, r), block3(), 0, s>>>(g, r.kbeg, o);
+    k_identity<<<grid3(g.ni, g.nj, r), block3(), 0, s>>>(g, r.kbeg, r.kend, o);
     count_launch();
     return cudaGetLastError();
 }
