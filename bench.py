@@ -154,7 +154,7 @@ def run_reference_arm(args):
                                    "has no CPU advection path, so this is the C restatement of its CUDA kernels (OpenMP)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -180,7 +180,7 @@ def run_gpu(args):
 
     if world > 1:
         from gpufluidsimulation_b200.zslab import ZSlabAdvection3D
-        solver = ZSlabAdvection3D(n, n, n, h, 1.0, rank=rank, world=world, halo=args.halo)
+        solver = ZSlabAdvection3D(n, n, n, h, 1.0, rank=rank, world=world, halo=args.halo, transport=args.transport)
     else:
         solver = BimocqAdvection3D(n, n, n, h, 1.0)
 
@@ -210,6 +210,8 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step(frame); frame += 1
     barrier()
+    if getattr(solver, "stepper", None) is not None:
+        solver.stepper.prof = {}
     solver.timing_enable(True)
     solver.timing_read()
     launches0 = lib.bmq_kernel_launch_count()
@@ -288,7 +290,7 @@ def run_gpu(args):
             "config": {"workload": f"BiMocq3D smoke plume {n}^3 (velocity + density + temperature), maps + 3 velocity "
                                    "components + 2 scalars per step",
                        "grid": [n, n, n], "dt": DT, "cfl_frame": CFL, "n_sub_mean": n_sub, "blend_coeff": 1.0,
-                       "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo {args.halo}",
+                       "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo {args.halo}, exchange={args.transport}",
                        "l2_policy": "inputs larger than L2 (537 MB per field vs 126 MB L2), no flush needed"},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         }
@@ -316,8 +318,10 @@ def run_gpu(args):
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.ref_size}^3 plume, 2 steps ({sec:.1f} s/step): C restatement of the reference "
                                           "CUDA kernels with OpenMP (the 3D reference has no CPU advection path)"}
+    if world > 1 and rank == 0 and getattr(solver, "stepper", None) is not None and solver.stepper.profile:
+        print("ZSLAB_PROFILE", {k: round(v, 4) for k, v in solver.stepper.prof.items()}, file=sys.stderr)
     if line is not None:
-        print(json.dumps(line))
+        emit(line)
     solver.close()
     if world > 1:
         dist.destroy_process_group()
@@ -395,13 +399,33 @@ def measure_e2e(solver, torch, n, args, frame):
             "path": "bmq3d_advect_host + bmq3d_accumulate_host (C ABI), pinned host buffers"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Write the ONE JSON line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print on stdout behind our back (NCCL writes its version banner there); the driver
+    # reads exactly one JSON line, so fd 1 is pointed at stderr for the whole run and only emit()
+    # writes to the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--halo", type=int, default=24)
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="z-slab halo exchange: P2P copies or NCCL send/recv")
     ap.add_argument("--ref-size", type=int, default=64, dest="ref_size")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")

@@ -67,6 +67,7 @@ FIELD_NAMES = [
 FIELD = {n: i for i, n in enumerate(FIELD_NAMES)}
 FIELD.update({n: 64 + i for i, n in enumerate(
     ["U_ADV", "V_ADV", "W_ADV", "RHO_ADV", "T_ADV", "U_ERR", "V_ERR", "W_ERR", "RHO_ERR", "T_ERR"])})
+FIELD.update({f"TMPMAP{i}": 80 + i for i in range(6)})
 
 N_TIMING_SLOTS = 16
 
@@ -96,6 +97,10 @@ _PROTOS = {
     "bmq_clear_error": (_I, []),
     "bmq_version": (C.c_char_p, []),
     "bmq_kernel_launch_count": (C.c_ulonglong, []),
+    "bmq_ipc_export": (_I, [C.c_void_p, C.c_void_p]),
+    "bmq_ipc_open": (_I, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bmq_ipc_close": (_I, [C.c_void_p]),
+    "bmq_copy_async": (_I, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gpu_solve_forward": (None, [_F] * 6 + [_f, _I, _I, _I, _f, _f]),
     "gpu_solve_backwardDMC": (None, [_F] * 9 + [_f, _I, _I, _I, _f]),
     "gpu_advect_velocity": (None, [_F] * 9 + [_f, _I, _I, _I, C.c_bool]),

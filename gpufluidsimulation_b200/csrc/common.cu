@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -66,6 +67,40 @@ int bmq_clear_error(void)
     bmq::g_err_code = BMQ_OK;
     bmq::g_err_msg.clear();
     return c;
+}
+
+int bmq_ipc_export(const void *dev_ptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!dev_ptr || !handle) return bmq::set_error(BMQ_ERR_ARG, "bmq_ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    BMQ_CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    return BMQ_OK;
+}
+
+int bmq_ipc_open(const unsigned char handle[64], void **dev_ptr)
+{
+    if (!handle || !dev_ptr) return bmq::set_error(BMQ_ERR_ARG, "bmq_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    BMQ_CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BMQ_OK;
+}
+
+int bmq_ipc_close(void *dev_ptr)
+{
+    if (!dev_ptr) return BMQ_OK;
+    BMQ_CK(cudaIpcCloseMemHandle(dev_ptr));
+    return BMQ_OK;
+}
+
+int bmq_copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (bytes == 0) return BMQ_OK;
+    if (!dst || !src) return bmq::set_error(BMQ_ERR_ARG, "bmq_copy_async: null pointer");
+    BMQ_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return BMQ_OK;
 }
 
 const char *bmq_version(void) { return "bimocq_b200 0.1 (sm_100a)"; }

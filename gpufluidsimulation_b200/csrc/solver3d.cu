@@ -98,6 +98,7 @@ Field *field_of(bmq3d_solver *s, int id)
 {
     if (id >= 0 && id < BMQ_F_COUNT) return &s->f[id];
     if (id >= SCRATCH_BASE && id < SCRATCH_BASE + N_SCRATCH) return &s->scratch[id - SCRATCH_BASE];
+    if (id >= BMQ_F_TMPMAP0 && id <= BMQ_F_TMPMAP5) return &s->tmpmap[id - BMQ_F_TMPMAP0];
     return nullptr;
 }
 

@@ -45,6 +45,15 @@ const char *bmq_version(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 unsigned long long bmq_kernel_launch_count(void);
 
+/* ---- peer-memory plumbing for the z-slab halo exchange over NVLink (one process per GPU).
+ * bmq_ipc_export: CUDA IPC handle (64 bytes) of the allocation `dev_ptr` is the base of;
+ * bmq_ipc_open: map a peer process's allocation into this process (lazy peer access);
+ * bmq_copy_async: stream-ordered device-to-device copy that accepts peer-mapped pointers. */
+int bmq_ipc_export(const void *dev_ptr, unsigned char handle[64]);
+int bmq_ipc_open(const unsigned char handle[64], void **dev_ptr);
+int bmq_ipc_close(void *dev_ptr);
+int bmq_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+
 /* ------------------------------------------------------------------ legacy drop-in symbols */
 /* replaces GPU_Advection.h:26-28 (def. GPU_kernel.cu:567-574): psi <- trace(psi, +dt), in place */
 void gpu_solve_forward(float *u, float *v, float *w, float *x_fwd, float *y_fwd, float *z_fwd,
@@ -211,7 +220,9 @@ int bmq3d_stage_accumulate(bmq3d_solver *s, int which);
 int bmq3d_stage_reinit(bmq3d_solver *s, int which, int phase);        /* phase 0: rotate+identity; 1: post-accumulate */
 /* Scratch fields the slab driver must also exchange (ids continue after BMQ_F_COUNT). */
 enum { BMQ_F_U_ADV = 64, BMQ_F_V_ADV, BMQ_F_W_ADV, BMQ_F_RHO_ADV, BMQ_F_T_ADV,
-       BMQ_F_U_ERR, BMQ_F_V_ERR, BMQ_F_W_ERR, BMQ_F_RHO_ERR, BMQ_F_T_ERR };
+       BMQ_F_U_ERR, BMQ_F_V_ERR, BMQ_F_W_ERR, BMQ_F_RHO_ERR, BMQ_F_T_ERR,
+       /* the six DMC ping-pong buffers (they rotate with the backward maps) */
+       BMQ_F_TMPMAP0 = 80, BMQ_F_TMPMAP1, BMQ_F_TMPMAP2, BMQ_F_TMPMAP3, BMQ_F_TMPMAP4, BMQ_F_TMPMAP5 };
 
 /* ------------------------------------------------------------------ handle API (2D)
  * The 2D reference (src/bimocq2D) is CPU code with no device seam; this API is the seam behind
