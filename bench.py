@@ -246,14 +246,14 @@ def run_gpu(args):
     own_frac = 1.0 / world
     # algorithmic bytes per LAUNCH (DESIGN.md "Kernels"): fp32 arrays a launch must read/write once
     alg = {
-        "accumulate_velocity": ("k_cumulate<NF=1,NCH=2>", 7 * 4 * faces["u"] * own_frac),   # psi3 + d_ext + d_proj + init R/W
-        "advect_velocity": ("k_advect<NF=1>", 5 * 4 * faces["u"] * own_frac),               # chi3 + init + out
-        "error_velocity": ("k_error<NF=1>", 6 * 4 * faces["u"] * own_frac),                 # psi3 + f_adv + init + e0
-        "apply_velocity": ("k_apply_clamp<NF=1>", 6 * 4 * faces["u"] * own_frac),           # chi3 + e0 + f_adv + out
-        "advect_scalars": ("k_advect<NF=2>", 7 * 4 * faces["c"] * own_frac),
-        "error_scalars": ("k_error<NF=2>", 9 * 4 * faces["c"] * own_frac),
-        "apply_scalars": ("k_apply_clamp<NF=2>", 9 * 4 * faces["c"] * own_frac),
-        "accumulate_scalars": ("k_cumulate<NF=2,NCH=1>", 9 * 4 * faces["c"] * own_frac),
+        "accumulate_velocity": ("k_cumulate_win<NF=1,NCH=2>", 7 * 4 * faces["u"] * own_frac),   # psi3 + d_ext + d_proj + init R/W
+        "advect_velocity": ("k_advect_win<NF=1>", 5 * 4 * faces["u"] * own_frac),               # chi3 + init + out
+        "error_velocity": ("k_error_win<NF=1>", 6 * 4 * faces["u"] * own_frac),                 # psi3 + f_adv + init + e0
+        "apply_velocity": ("k_apply_clamp_win<NF=1>", 6 * 4 * faces["u"] * own_frac),           # chi3 + e0 + f_adv + out
+        "advect_scalars": ("k_advect_win<NF=2>", 7 * 4 * faces["c"] * own_frac),
+        "error_scalars": ("k_error_win<NF=2>", 9 * 4 * faces["c"] * own_frac),
+        "apply_scalars": ("k_apply_clamp_win<NF=2>", 9 * 4 * faces["c"] * own_frac),
+        "accumulate_scalars": ("k_cumulate_win<NF=2,NCH=1>", 9 * 4 * faces["c"] * own_frac),
         "dmc_backward": ("k_dmc<NMAP=2>", 15 * 4 * faces["c"] * own_frac),
         "forward": ("k_forward<NMAP=2>", 15 * 4 * faces["c"] * own_frac),
         "distortion": ("k_estimate<NMAP=2>", 12 * 4 * faces["c"] * own_frac),
