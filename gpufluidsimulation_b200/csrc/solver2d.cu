@@ -129,6 +129,23 @@ __device__ V2 solve_ode(const G2 &g, const float *u, const float *v, float dt, V
     return pos2;
 }
 
+// First round of solveODE only: one full step against two half steps.  Returns true (and the
+// result) when the reference's loop would stop right there, which is the case almost everywhere;
+// the few cells that keep halving (next to walls, where traceRK3's clamp and getVelocity's
+// zero-outside rule make the trace non-smooth; up to 254 RK3 steps) are deferred to a compacted
+// second pass so that they do not hold whole warps of converged cells hostage.
+__device__ __forceinline__ bool solve_ode_quick(const G2 &g, const float *u, const float *v, float dt, V2 pos, V2 &out)
+{
+    const V2 pos1 = trace_rk3(g, u, v, dt, pos);
+    const float ddt = (float)((double)dt / 2.0);
+    V2 pos2 = trace_rk3(g, u, v, ddt, pos);
+    pos2 = trace_rk3(g, u, v, ddt, pos2);
+    const float dx = FS(pos2.x, pos1.x), dy = FS(pos2.y, pos1.y);
+    const float d = sqrtf(FA(FM(dx, dx), FM(dy, dy)));
+    out = pos2;
+    return !((double)d > 0.0001 * (double)g.h);
+}
+
 __device__ __forceinline__ void clamp_pos(const G2 &g, V2 &p)   // BimocqSolver2D.h:128-132
 {
     p.x = fminf(fmaxf(g.h, p.x), FS(FM((float)g.ni, g.h), g.h));
@@ -184,15 +201,36 @@ __device__ __forceinline__ V2 map_through(const G2 &g, const float *mx, const fl
     const int idx = i + (fni) * j;
 
 // ---------------------------------------------------------------- kernels
-// updateForward, :1228-1240 (all cells)
-__global__ void __launch_bounds__(256) k2_forward(G2 g, const float *u, const float *v, float *fx, float *fy, float dt)
+// Work list of the cells whose solveODE did not converge in the first round.
+struct WorkList {
+    int *count;   // device counter
+    int *items;   // flat element indices
+};
+__device__ __forceinline__ void defer(const WorkList &wl, int idx) { wl.items[atomicAdd(wl.count, 1)] = idx; }
+
+// updateForward, :1228-1240 (all cells).  SLOW = false: every cell, first solveODE round only,
+// non-converged cells deferred; SLOW = true: the deferred cells, full solveODE.
+template <bool SLOW>
+__global__ void __launch_bounds__(256) k2_forward(G2 g, const float *u, const float *v, float *fx, float *fy, float dt, WorkList wl)
 {
-    IJ(g.ni, g.nj)
-    V2 p = {fx[idx], fy[idx]};
-    p = solve_ode(g, u, v, dt, p);
-    clamp_pos(g, p);
-    fx[idx] = p.x;
-    fy[idx] = p.y;
+    if (!SLOW) {
+        IJ(g.ni, g.nj)
+        V2 p = {fx[idx], fy[idx]}, q;
+        if (!solve_ode_quick(g, u, v, dt, p, q)) { defer(wl, idx); return; }
+        clamp_pos(g, q);
+        fx[idx] = q.x;
+        fy[idx] = q.y;
+    } else {
+        const int n = *wl.count;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+            const int idx = wl.items[e];
+            V2 p = {fx[idx], fy[idx]};
+            p = solve_ode(g, u, v, dt, p);
+            clamp_pos(g, p);
+            fx[idx] = p.x;
+            fy[idx] = p.y;
+        }
+    }
 }
 
 // one sub-step of updateBackward (:1242-1259): semiLagAdvectDMC for x and y maps from one back-trace
@@ -209,15 +247,28 @@ k2_backward(G2 g, const float *u, const float *v, const float *bx, const float *
     oy[idx] = sample_field(by, g.ni, g.nj, g.h, sx, sy);
 }
 
-// semiLagAdvect, :110-123
+// semiLagAdvect, :110-123 (same two-pass scheme as k2_forward)
+template <bool SLOW>
 __global__ void __launch_bounds__(256)
-k2_semilag(G2 g, const float *u, const float *v, const float *src, float *dst, int fni, int fnj, float offx, float offy, float dt)
+k2_semilag(G2 g, const float *u, const float *v, const float *src, float *dst, int fni, int fnj, float offx, float offy,
+           float dt, WorkList wl)
 {
-    IJ(fni, fnj)
     const float ox = FM(g.h, offx), oy = FM(g.h, offy);
-    V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)};
-    V2 b = solve_ode(g, u, v, -dt, pos);
-    dst[idx] = sample_field(src, fni, fnj, g.h, FS(b.x, ox), FS(b.y, oy));
+    if (!SLOW) {
+        IJ(fni, fnj)
+        V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)}, b;
+        if (!solve_ode_quick(g, u, v, -dt, pos, b)) { defer(wl, idx); return; }
+        dst[idx] = sample_field(src, fni, fnj, g.h, FS(b.x, ox), FS(b.y, oy));
+    } else {
+        const int n = *wl.count;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+            const int idx = wl.items[e];
+            const int i = idx % fni, j = idx / fni;
+            V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)};
+            V2 b = solve_ode(g, u, v, -dt, pos);
+            dst[idx] = sample_field(src, fni, fnj, g.h, FS(b.x, ox), FS(b.y, oy));
+        }
+    }
 }
 
 struct AdvectArgs {
@@ -449,6 +500,11 @@ struct bmq2d_solver {
     float *f[BMQ2_F_COUNT] = {};
     int fni[BMQ2_F_COUNT], fnj[BMQ2_F_COUNT];
     float *d_red = nullptr, *h_red = nullptr;
+    int *d_wl = nullptr;       // 6 work lists of wl_stride ints: [0] = counter, [1..] = deferred element indices
+    size_t wl_stride = 0;
+    cudaStream_t side[6] = {};
+    cudaEvent_t ev_quick = nullptr, ev_side[6] = {};
+    int pending_slow = 0;      // bit w set: slow pass w has been recorded on side[w]
     int lastremeshing = 0, rho_lastremeshing = 0, total_resample = 0, total_scalar_resample = 0;
     bool levelset = false;
     float cfl = 0.f;
@@ -519,12 +575,67 @@ int max_vel(bmq2d_solver *s, float *out)
     return BMQ_OK;
 }
 
-int update_maps(bmq2d_solver *s, float dt, int fx, int fy, int bx, int by)
+WorkList worklist(bmq2d_solver *s, int w) { return WorkList{s->d_wl + w * s->wl_stride, s->d_wl + w * s->wl_stride + 1}; }
+
+// The solveODE-based kernels run in two passes (see solve_ode_quick).  The quick passes go on the
+// solver's stream; the six compacted slow passes (2 forward maps, 4 semi-Lagrangian fields) are
+// independent of each other and of the DMC backward update, and each is one long dependent chain
+// of up to 254 RK3 steps, so they are launched side by side on six side streams and joined before
+// the first consumer.
+int forward_quick(bmq2d_solver *s, float dt, int fx, int fy, int w)
 {
-    const float *u = s->f[BMQ2_F_U], *v = s->f[BMQ2_F_V];
-    k2_forward<<<grd(s->ni, s->nj), blk(), 0, s->stream>>>(s->g, u, v, s->f[fx], s->f[fy], dt);
+    WorkList wl = worklist(s, w);
+    BMQ_CK(cudaMemsetAsync(wl.count, 0, sizeof(int), s->stream));
+    k2_forward<false><<<grd(s->ni, s->nj), blk(), 0, s->stream>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, wl);
     L2D(s);
     BMQ_CK(cudaGetLastError());
+    return BMQ_OK;
+}
+int forward_slow(bmq2d_solver *s, float dt, int fx, int fy, int w)
+{
+    BMQ_CK(cudaStreamWaitEvent(s->side[w], s->ev_quick, 0));
+    k2_forward<true><<<148, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, worklist(s, w));
+    L2D(s);
+    BMQ_CK(cudaGetLastError());
+    BMQ_CK(cudaEventRecord(s->ev_side[w], s->side[w]));
+    s->pending_slow |= 1 << w;
+    return BMQ_OK;
+}
+int semilag_quick(bmq2d_solver *s, int src, int dst, float dt, int w)
+{
+    FieldGeom q = geom(s, kind_of(src));
+    WorkList wl = worklist(s, w);
+    BMQ_CK(cudaMemsetAsync(wl.count, 0, sizeof(int), s->stream));
+    k2_semilag<false><<<grd(q.fni, q.fnj), blk(), 0, s->stream>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst],
+                                                               q.fni, q.fnj, q.offx, q.offy, dt, wl);
+    L2D(s);
+    BMQ_CK(cudaGetLastError());
+    return BMQ_OK;
+}
+int semilag_slow(bmq2d_solver *s, int src, int dst, float dt, int w)
+{
+    FieldGeom q = geom(s, kind_of(src));
+    BMQ_CK(cudaStreamWaitEvent(s->side[w], s->ev_quick, 0));
+    k2_semilag<true><<<148, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst], q.fni, q.fnj,
+                                               q.offx, q.offy, dt, worklist(s, w));
+    L2D(s);
+    BMQ_CK(cudaGetLastError());
+    BMQ_CK(cudaEventRecord(s->ev_side[w], s->side[w]));
+    s->pending_slow |= 1 << w;
+    return BMQ_OK;
+}
+int join_slow(bmq2d_solver *s)
+{
+    for (int w = 0; w < 6; ++w)
+        if (s->pending_slow & (1 << w)) BMQ_CK(cudaStreamWaitEvent(s->stream, s->ev_side[w], 0));
+    s->pending_slow = 0;
+    return BMQ_OK;
+}
+
+// updateBackward, :1242-1259
+int update_backward(bmq2d_solver *s, float dt, int bx, int by)
+{
+    const float *u = s->f[BMQ2_F_U], *v = s->f[BMQ2_F_V];
     float substep = s->cfl, T = dt, t = 0.f;
     int n = 0;
     while (t < T) {
@@ -539,16 +650,6 @@ int update_maps(bmq2d_solver *s, float dt, int fx, int fy, int bx, int by)
         if (++n > 4096) return bmq::set_error(BMQ_ERR_ARG, "bmq2d: more than 4096 CFL sub-steps");
     }
     s->stats.n_substeps = n;
-    return BMQ_OK;
-}
-
-int semilag(bmq2d_solver *s, int src, int dst, float dt)
-{
-    FieldGeom q = geom(s, kind_of(src));
-    k2_semilag<<<grd(q.fni, q.fnj), blk(), 0, s->stream>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst], q.fni,
-                                                        q.fnj, q.offx, q.offy, dt);
-    L2D(s);
-    BMQ_CK(cudaGetLastError());
     return BMQ_OK;
 }
 
@@ -664,6 +765,13 @@ int bmq2d_create(int ni, int nj, float h, float blend_coeff, bmq2d_solver **out)
         if (st == BMQ_OK) st = bmq::check_cuda(cudaMemset(s->f[id], 0, bytes), "cudaMemset", __FILE__, __LINE__);
     }
     if (st == BMQ_OK) st = bmq::check_cuda(cudaMalloc(&s->d_red, 4 * sizeof(float)), "cudaMalloc", __FILE__, __LINE__);
+    s->wl_stride = (size_t)(ni + 1) * (nj + 1) + 1;
+    if (st == BMQ_OK) st = bmq::check_cuda(cudaMalloc(&s->d_wl, sizeof(int) * 6 * s->wl_stride), "cudaMalloc", __FILE__, __LINE__);
+    for (int w = 0; w < 6 && st == BMQ_OK; ++w) {
+        st = bmq::check_cuda(cudaStreamCreateWithFlags(&s->side[w], cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__);
+        if (st == BMQ_OK) st = bmq::check_cuda(cudaEventCreateWithFlags(&s->ev_side[w], cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
+    }
+    if (st == BMQ_OK) st = bmq::check_cuda(cudaEventCreateWithFlags(&s->ev_quick, cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
     if (st == BMQ_OK) st = bmq::check_cuda(cudaMallocHost(&s->h_red, 4 * sizeof(float)), "cudaMallocHost", __FILE__, __LINE__);
     if (st == BMQ_OK) st = bmq2d_reset(s);
     if (st != BMQ_OK) { bmq2d_destroy(s); return st; }
@@ -676,6 +784,12 @@ int bmq2d_destroy(bmq2d_solver *s)
     if (!s) return BMQ_OK;
     for (float *p : s->f) if (p) cudaFree(p);
     if (s->d_red) cudaFree(s->d_red);
+    if (s->d_wl) cudaFree(s->d_wl);
+    for (int w = 0; w < 6; ++w) {
+        if (s->side[w]) cudaStreamDestroy(s->side[w]);
+        if (s->ev_side[w]) cudaEventDestroy(s->ev_side[w]);
+    }
+    if (s->ev_quick) cudaEventDestroy(s->ev_quick);
     if (s->h_red) cudaFreeHost(s->h_red);
     delete s;
     return BMQ_OK;
@@ -753,12 +867,24 @@ int bmq2d_advect(bmq2d_solver *s, int frame, float dt)
     }
     s->cfl = s->h / fabsf(s->stats.max_vel_pre);
     s->stats.cfl = s->cfl;
-    if (!s->levelset) R2(update_maps(s, dt, BMQ2_F_FWD_X, BMQ2_F_FWD_Y, BMQ2_F_BWD_X, BMQ2_F_BWD_Y));
-    R2(update_maps(s, dt, BMQ2_F_SFWD_X, BMQ2_F_SFWD_Y, BMQ2_F_SBWD_X, BMQ2_F_SBWD_Y));
-    R2(semilag(s, BMQ2_F_RHO, BMQ2_F_RHO_SEMI, dt));
-    R2(semilag(s, BMQ2_F_T, BMQ2_F_T_SEMI, dt));
-    R2(semilag(s, BMQ2_F_U, BMQ2_F_U_SEMI, dt));
-    R2(semilag(s, BMQ2_F_V, BMQ2_F_V_SEMI, dt));
+    // quick passes of every solveODE-based kernel, then their slow passes side by side, overlapped
+    // with the DMC backward updates (which depend on none of them)
+    if (!s->levelset) R2(forward_quick(s, dt, BMQ2_F_FWD_X, BMQ2_F_FWD_Y, 0));
+    R2(forward_quick(s, dt, BMQ2_F_SFWD_X, BMQ2_F_SFWD_Y, 1));
+    R2(semilag_quick(s, BMQ2_F_RHO, BMQ2_F_RHO_SEMI, dt, 2));
+    R2(semilag_quick(s, BMQ2_F_T, BMQ2_F_T_SEMI, dt, 3));
+    R2(semilag_quick(s, BMQ2_F_U, BMQ2_F_U_SEMI, dt, 4));
+    R2(semilag_quick(s, BMQ2_F_V, BMQ2_F_V_SEMI, dt, 5));
+    BMQ_CK(cudaEventRecord(s->ev_quick, s->stream));
+    if (!s->levelset) R2(forward_slow(s, dt, BMQ2_F_FWD_X, BMQ2_F_FWD_Y, 0));
+    R2(forward_slow(s, dt, BMQ2_F_SFWD_X, BMQ2_F_SFWD_Y, 1));
+    R2(semilag_slow(s, BMQ2_F_RHO, BMQ2_F_RHO_SEMI, dt, 2));
+    R2(semilag_slow(s, BMQ2_F_T, BMQ2_F_T_SEMI, dt, 3));
+    R2(semilag_slow(s, BMQ2_F_U, BMQ2_F_U_SEMI, dt, 4));
+    R2(semilag_slow(s, BMQ2_F_V, BMQ2_F_V_SEMI, dt, 5));
+    if (!s->levelset) R2(update_backward(s, dt, BMQ2_F_BWD_X, BMQ2_F_BWD_Y));
+    R2(update_backward(s, dt, BMQ2_F_SBWD_X, BMQ2_F_SBWD_Y));
+    R2(join_slow(s));
     R2(copyf(s, BMQ2_F_U_PRESAVE, BMQ2_F_U));
     R2(copyf(s, BMQ2_F_V_PRESAVE, BMQ2_F_V));
     if (!s->levelset) {
