@@ -6,7 +6,7 @@ MapperBase semantics), on the same B200, same inputs.
 * per-step parity: both sides start every step from the identical state (the reference side's)
   -> relative L-inf <= 1e-5 on u, v, w, rho, T, the init buffers and all maps, and identical
   reinitialisation decisions;
-* free-running drift over 30 steps is measured and bounded loosely: the reference's DMC formula
+* free-running drift over 100 steps is measured and bounded loosely: the reference's DMC formula
   1 - exp(-a s) (GPU_kernel.cu:194-196) amplifies last-ulp differences of the previous step's
   velocity by up to 6e-8/(a s), so trajectories separate at velocity extrema no matter how the
   arithmetic is arranged; the fraction of cells within 1e-5 is reported next to the L-inf."""
@@ -114,7 +114,7 @@ def test_free_running_drift_vs_reference_kernels(cuda, reflib):
     sg.set_initial(u, v, w, rho, T)
     rf, gf = [], []
     report = []
-    for frame in range(30):
+    for frame in range(100):
         ref.advect(frame, dt); sg.advect(frame, dt)
         cur_r = [t.cpu().numpy() for t in ref.cur]
         cur_g = [sg.download(n) for n in NAMES]
@@ -128,7 +128,7 @@ def test_free_running_drift_vs_reference_kernels(cuda, reflib):
         errs = [rel_linf(g, r) for g, r in zip(cur_g, cur_r)]
         within = min(float((np.abs(g - r) <= 1e-5 * np.abs(r).max()).mean()) for g, r in zip(cur_g, cur_r))
         report.append((frame, max(errs), within))
-    for frame, e, wi in report[::5] + report[-1:]:
+    for frame, e, wi in report[::20] + report[-1:]:
         print(f"free-running frame {frame:2d}: rel Linf {e:.2e}, cells within 1e-5: {100 * wi:.3f}%")
     print("reinit frames: ours", gf, "reference", rf)
     # the first ten reinitialisations must coincide; later ones may shift by a frame when the
