@@ -55,6 +55,9 @@ struct bmq3d_solver {
     bool vel_reinit = false, scalar_reinit = false;
     bmq3d_stats stats;
     bool semi_alloc = false;
+    // copy streams + events of the host-buffer path (bmq3d_*_host): transfers overlap the stages
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_copy[12] = {};
     // optional per-stage CUDA-event timing (bmq3d_timing_*): pairs recorded on `stream`
     bool timing = false;
     struct Span { int slot; cudaEvent_t a, b; };
@@ -496,6 +499,9 @@ int bmq3d_destroy(bmq3d_solver *s)
     for (auto &fd : s->f) if (fd.alloc) cudaFree(fd.alloc);
     for (auto &fd : s->scratch) if (fd.alloc) cudaFree(fd.alloc);
     for (auto &fd : s->tmpmap) if (fd.alloc) cudaFree(fd.alloc);
+    if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
+    if (s->s_d2h) cudaStreamDestroy(s->s_d2h);
+    for (auto e : s->ev_copy) if (e) cudaEventDestroy(e);
     for (auto &sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : s->event_pool) cudaEventDestroy(e);
     if (s->d_red) cudaFree(s->d_red);
@@ -702,20 +708,65 @@ int bmq3d_get_stats(bmq3d_solver *s, bmq3d_stats *out)
     return BMQ_OK;
 }
 
+static int ensure_copy_streams(bmq3d_solver *s)
+{
+    if (s->s_h2d) return BMQ_OK;
+    BMQ_CK(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
+    BMQ_CK(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
+    for (auto &e : s->ev_copy) BMQ_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return BMQ_OK;
+}
+
+static int upload_async(bmq3d_solver *s, Field &fd, const float *host, cudaEvent_t done)
+{
+    BMQ_CK(cudaMemcpyAsync(fd.alloc, host, fd.stored_elems() * sizeof(float), cudaMemcpyHostToDevice, s->s_h2d));
+    BMQ_CK(cudaEventRecord(done, s->s_h2d));
+    return BMQ_OK;
+}
+
+// Phase A through host buffers.  Transfers run on their own streams and overlap the stages:
+// only u,v,w are uploaded (phase A never reads the current density / temperature: they are pure
+// outputs of MapperBase::advectField, Mapping.cpp:208-236); u,v,w travel back while the scalar
+// stages run.
 int bmq3d_advect_host(bmq3d_solver *s, int framenum, float dt, float *u, float *v, float *w, float *rho, float *T)
 {
     NEED(s);
+    if (!(dt > 0.f)) return set_error(BMQ_ERR_ARG, "bmq3d_advect_host: dt must be positive");
     float *host[5] = {u, v, w, rho, T};
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < 5; ++c)
         if (!host[c]) return set_error(BMQ_ERR_ARG, "bmq3d_advect_host: null field pointer %d", c);
-        Field &fd = s->f[BMQ_F_U + c];
-        BMQ_CK(cudaMemcpyAsync(fd.alloc, host[c], fd.stored_elems() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    RET_IF(ensure_copy_streams(s));
+    cudaEvent_t *ev = s->ev_copy;
+    BMQ_CK(cudaEventRecord(ev[0], s->stream));                  // everything queued so far
+    BMQ_CK(cudaStreamWaitEvent(s->s_h2d, ev[0], 0));
+    for (int c = 0; c < 3; ++c) RET_IF(upload_async(s, s->f[BMQ_F_U + c], host[c], ev[1]));
+    BMQ_CK(cudaStreamWaitEvent(s->stream, ev[1], 0));
+    float mabs = 0.f;
+    RET_IF(stage_maxvel(s, &mabs));
+    set_cfl(s, framenum, mabs);
+    float Tt = 0.f, substep = s->cfldt;
+    int n = 0;
+    while (Tt < dt) {
+        if (Tt + substep > dt) substep = dt - Tt;
+        RET_IF(stage_dmc(s, substep));
+        Tt += substep;
+        if (++n > 4096) return set_error(BMQ_ERR_ARG, "bmq3d_advect_host: more than 4096 CFL sub-steps");
     }
-    RET_IF(bmq3d_advect(s, framenum, dt, 0));
-    for (int c = 0; c < 5; ++c) {
-        Field &fd = s->f[BMQ_F_U + c];
-        BMQ_CK(cudaMemcpyAsync(host[c], fd.alloc, fd.stored_elems() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    s->stats.n_substeps = n;
+    RET_IF(stage_forward(s, dt));
+    for (int which = 0; which < 2; ++which) {
+        RET_IF(stage_advect(s, which));
+        RET_IF(stage_error(s, which));
+        RET_IF(stage_apply(s, which));
+        RET_IF(stage_blend(s, which));
+        BMQ_CK(cudaEventRecord(ev[2 + which], s->stream));
+        BMQ_CK(cudaStreamWaitEvent(s->s_d2h, ev[2 + which], 0));
+        for (int c = which == 0 ? 0 : 3; c < (which == 0 ? 3 : 5); ++c) {
+            Field &fd = s->f[BMQ_F_U + c];
+            BMQ_CK(cudaMemcpyAsync(host[c], fd.alloc, fd.stored_elems() * sizeof(float), cudaMemcpyDeviceToHost, s->s_d2h));
+        }
     }
+    BMQ_CK(cudaStreamSynchronize(s->s_d2h));
     BMQ_CK(cudaStreamSynchronize(s->stream));
     return BMQ_OK;
 }
@@ -729,27 +780,52 @@ int bmq3d_accumulate_host(bmq3d_solver *s, int framenum, float dt, const float *
     const float *fin[5] = {u_final, v_final, w_final, rho_final, T_final};
     for (int c = 0; c < 5; ++c)
         if (!fin[c] || (c < 3 && !forced[c])) return set_error(BMQ_ERR_ARG, "bmq3d_accumulate_host: null field %d", c);
+    RET_IF(ensure_copy_streams(s));
+    cudaEvent_t *ev = s->ev_copy;
     // The change fields are formed on the device exactly as the reference forms them on the host
     // (BimocqSolver.cpp:149-162): d_ext = forced - advected, d_proj = final - forced,
     // d_scalar = final - advected; the device copy of the current fields becomes `final`.
+    // Uploads go to staging buffers on the copy stream (forced -> D*_PROJ, final -> the advect
+    // scratch, which is free in phase B) and overlap the distortion kernel and each other's
+    // consumers; the scratch is cleared afterwards because it must keep its zero ring.
+    BMQ_CK(cudaEventRecord(ev[0], s->stream));
+    BMQ_CK(cudaStreamWaitEvent(s->s_h2d, ev[0], 0));
     for (int c = 0; c < 3; ++c) {
-        Field &cur = s->f[BMQ_F_U + c], &ext = s->f[BMQ_F_DU_EXT + c], &proj = s->f[BMQ_F_DU_PROJ + c];
-        const size_t n = cur.stored_elems();
-        BMQ_CK(cudaMemcpyAsync(proj.alloc, forced[c], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-        BMQ_CK(launch_add_field(s->stream, ext.alloc, proj.alloc, cur.alloc, -1.f, n));     // forced - advected
-        BMQ_CK(cudaMemcpyAsync(cur.alloc, fin[c], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-        BMQ_CK(launch_add_field(s->stream, proj.alloc, cur.alloc, proj.alloc, -1.f, n));    // final - forced
+        RET_IF(upload_async(s, s->f[BMQ_F_DU_PROJ + c], forced[c], ev[4 + 2 * c]));
+        RET_IF(upload_async(s, s->scratch[c], fin[c], ev[5 + 2 * c]));
     }
-    for (int c = 0; c < 2; ++c) {
-        Field &cur = s->f[BMQ_F_RHO + c], &ext = s->f[BMQ_F_DRHO_EXT + c], &tmp = s->scratch[3 + c];
-        const size_t n = cur.stored_elems();
-        BMQ_CK(cudaMemcpyAsync(tmp.alloc, fin[3 + c], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-        BMQ_CK(launch_add_field(s->stream, ext.alloc, tmp.alloc, cur.alloc, -1.f, n));      // final - advected
-        BMQ_CK(cudaMemcpyAsync(cur.alloc, tmp.alloc, n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        // the advect scratch must keep its zero ring (see file header): restore it by clearing
-        BMQ_CK(cudaMemsetAsync(tmp.alloc, 0, n * sizeof(float), s->stream));
+    for (int c = 3; c < 5; ++c) RET_IF(upload_async(s, s->scratch[c], fin[c], ev[7 + c]));
+    float vd2 = 0, sd2 = 0, dz = 0;
+    RET_IF(stage_distortion(s, &vd2, &sd2, &dz));
+    s->stats.max_disp_z = dz;
+    decide(s, framenum, dt, vd2, sd2);
+    for (int c = 0; c < 3; ++c) {
+        Field &cur = s->f[BMQ_F_U + c], &ext = s->f[BMQ_F_DU_EXT + c], &proj = s->f[BMQ_F_DU_PROJ + c], &stg = s->scratch[c];
+        const size_t nel = cur.stored_elems();
+        BMQ_CK(cudaStreamWaitEvent(s->stream, ev[4 + 2 * c], 0));
+        BMQ_CK(launch_add_field(s->stream, ext.alloc, proj.alloc, cur.alloc, -1.f, nel));     // forced - advected
+        BMQ_CK(cudaStreamWaitEvent(s->stream, ev[5 + 2 * c], 0));
+        BMQ_CK(launch_add_field(s->stream, proj.alloc, stg.alloc, proj.alloc, -1.f, nel));    // final - forced
+        BMQ_CK(cudaMemcpyAsync(cur.alloc, stg.alloc, nel * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        BMQ_CK(cudaMemsetAsync(stg.alloc, 0, nel * sizeof(float), s->stream));
     }
-    RET_IF(bmq3d_accumulate(s, framenum, dt));
+    RET_IF(stage_accumulate(s, 0));
+    for (int c = 3; c < 5; ++c) {
+        Field &cur = s->f[BMQ_F_U + c], &ext = s->f[BMQ_F_DU_EXT + c], &stg = s->scratch[c];
+        const size_t nel = cur.stored_elems();
+        BMQ_CK(cudaStreamWaitEvent(s->stream, ev[7 + c], 0));
+        BMQ_CK(launch_add_field(s->stream, ext.alloc, stg.alloc, cur.alloc, -1.f, nel));      // final - advected
+        BMQ_CK(cudaMemcpyAsync(cur.alloc, stg.alloc, nel * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        BMQ_CK(cudaMemsetAsync(stg.alloc, 0, nel * sizeof(float), s->stream));
+    }
+    RET_IF(stage_accumulate(s, 1));
+    if (s->vel_reinit) {
+        RET_IF(stage_reinit(s, 0, 0));
+        RET_IF(stage_reinit(s, 0, 1));
+    }
+    if (s->scalar_reinit) RET_IF(stage_reinit(s, 1, 0));
+    s->stats.vel_reinit_count = s->vel_reinit_count;
+    s->stats.scalar_reinit_count = s->scalar_reinit_count;
     BMQ_CK(cudaStreamSynchronize(s->stream));
     return BMQ_OK;
 }

@@ -188,8 +188,9 @@ int bmq3d_timing_read(bmq3d_solver *s, float *ms_out, int *spans_out, int n_slot
 const char *bmq3d_timing_slot_name(int slot);
 
 /* Whole step through HOST buffers (the reference's host-orchestrated solver keeps its fields on
- * the host, Mapping.cpp:7-236).  bmq3d_advect_host uploads u,v,w,rho,T, runs phase A and
- * downloads the advected fields into the same arrays.  The caller then applies its forces and
+ * the host, Mapping.cpp:7-236).  bmq3d_advect_host uploads u,v,w (phase A never reads the current
+ * density / temperature, which are pure outputs of MapperBase::advectField), runs phase A and
+ * downloads the advected u,v,w,rho,T into the arrays; transfers overlap the stages.  The caller then applies its forces and
  * its projection on the host and hands bmq3d_accumulate_host the velocity after the external
  * forces (`*_forced`), the final velocity after projection and the final scalars; the change
  * fields are formed on the device exactly as BimocqSolver.cpp:149-162 forms them
