@@ -5,7 +5,7 @@
 // the launch covers global planes [kbeg,kend).  Interior guards are the reference's, in global
 // indices, so a slab rank computes exactly the values a single GPU would.
 //
-// Thread mapping: blockDim = (32, 8, 1); x -> i (coalesced rows), y -> j, blockIdx.z -> k.
+// Thread mapping: blockDim = (32, 4, 1); x -> i (coalesced rows), y -> j, blockIdx.z -> k.
 // No integer div/mod per thread (the reference decodes a flat index with two of each).
 #include "launch3d.h"
 #include "device3d.cuh"
@@ -35,10 +35,10 @@ Grid3 make_grid(int ni, int nj, int nk, float h)
     return g;
 }
 
-// CTA shape (32, BMQ_BY, BMQ_BZ), 256 threads.  A CTA that spans several z-planes shares the
+// CTA shape (32, BMQ_BY, BMQ_BZ); default 32x4x1 = 128 threads.  A CTA that spans several z-planes shares the
 // k-1/k/k+1 planes of the map windows and of the near-identity field gathers in L1.
 #ifndef BMQ_BY
-#define BMQ_BY 8
+#define BMQ_BY 4
 #endif
 #ifndef BMQ_BZ
 #define BMQ_BZ 1
@@ -286,7 +286,7 @@ k_apply_clamp(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<N
 // the map samples of the 8 sub-cell points come from one node window per map component
 // (quad_gather_win in device3d.cuh).  STAG: 0 centred, 1/2/3 = u/v/w faces (compile time).
 #ifndef BMQ_WIN_MINBLOCKS
-#define BMQ_WIN_MINBLOCKS 5   // <= 51 registers: 5 CTAs/SM hide the dependent map->field gather latency (A/B in profiles/r1_variants.txt)
+#define BMQ_WIN_MINBLOCKS 7   // 128-thread CTAs, >= 7 per SM (<= 73 registers, no spills): best of the A/B sweep in profiles/r1_variants.txt
 #endif
 #define BMQ_STAG_SETUP                                                                             \
     constexpr int DX = STAG == 1, DY = STAG == 2, DZ = STAG == 3;                                  \
@@ -299,7 +299,7 @@ k_apply_clamp(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<N
     const int idx = i + fi * (j + fj * k);
 
 template <bool P2, int STAG, int NF>
-__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
+__global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
 k_advect_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
 {
     BMQ_STAG_SETUP
@@ -314,7 +314,7 @@ k_advect_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> in
 }
 
 template <bool P2, int STAG, int NF>
-__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
+__global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
 k_error_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
 {
     BMQ_STAG_SETUP
@@ -329,7 +329,7 @@ k_error_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> e0, FieldSetRO<NF> src,
 }
 
 template <bool P2, int STAG, int NF, int NCH>
-__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
+__global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
 k_cumulate_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change, Coeffs<NCH> coeff, Map3 map)
 {
     BMQ_STAG_SETUP
@@ -354,7 +354,7 @@ k_cumulate_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> target, FieldSetRO<N
 }
 
 template <bool P2, int STAG, int NF>
-__global__ void __launch_bounds__(256, BMQ_WIN_MINBLOCKS)
+__global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
 k_apply_clamp_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> fadv, FieldSetRO<NF> e0, Map3 chi)
 {
     BMQ_STAG_SETUP

@@ -170,23 +170,20 @@ class PeerComm(DistComm):
         self.lib = slab_rank.solver.lib
         self.copy_stream = torch.cuda.Stream(device=device)
         self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+        from .capi import check
         n = len(self.ALLOC_NAMES)
         handles = torch.zeros((n, 64), dtype=torch.uint8)
         self.index_of_ptr = {}
-        self.geom = {}
         for i, name in enumerate(self.ALLOC_NAMES):
-            ptr, p0, npl, nx, ny = slab_rank.solver.field_info(name)
+            ptr = slab_rank.solver.field_info(name)[0]
             buf = (C.c_ubyte * 64)()
-            from .capi import check
             check(self.lib.bmq_ipc_export(C.c_void_p(ptr), buf), "bmq_ipc_export")
             handles[i] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
             self.index_of_ptr[ptr] = i
-        gathered = [torch.zeros_like(handles) for _ in range(world)]
-        self.dist.all_gather_object  # noqa: B018  (API presence check)
-        hd = handles.to(device)
-        gd = [torch.zeros_like(hd) for _ in range(world)]
-        self.dist.all_gather(gd, hd)
-        gathered = [g.cpu() for g in gd]
+        mine = handles.to(device)
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        self.dist.all_gather(everyone, mine)
+        gathered = [g.cpu() for g in everyone]
         self.peer = {}
         for nb in (rank - 1, rank + 1):
             if 0 <= nb < world:
@@ -194,10 +191,15 @@ class PeerComm(DistComm):
                 for i in range(n):
                     raw = (C.c_ubyte * 64).from_buffer_copy(bytes(gathered[nb][i].tolist()))
                     out = C.c_void_p()
-                    check(self.lib.bmq_ipc_open(raw, C.byref(out)), "bmq_ipc_open")
+                    check(self.lib.bmq_ipc_open(raw, C.byref(out)), "bmq_ipc_open")   # lazy peer access
                     ptrs.append(out.value)
                 self.peer[nb] = ptrs
         self.dist.barrier()
+
+    @staticmethod
+    def _check(status, what):
+        from .capi import check
+        check(status, what)
 
     def _stored_origin(self, rank):
         k0, _ = slab_bounds(self.r.nk, self.world, rank)
@@ -226,8 +228,7 @@ class PeerComm(DistComm):
                 dst = ptr + 4 * plane * (rng[0] - p0)
                 st = self.lib.bmq_copy_async(C.c_void_p(dst), C.c_void_p(src), 4 * plane * (rng[1] - rng[0]), cs)
                 if st != 0:
-                    from .capi import check
-                    check(st, "bmq_copy_async")
+                    self._check(st, "bmq_copy_async")
         done = torch.cuda.Event()
         done.record(self.copy_stream)
         return done
