@@ -10,7 +10,7 @@
  * Pinning: the reference ships no tests or golden vectors, so this
  * restatement is pinned against the reference's own kernels executed on a B200
  * (oracle/_ref/libref3d.so, built unmodified from GPU_kernel.cu by oracle/Makefile;
- * tests/test_oracle_vs_reference_gpu.py) and against golden fixtures generated from that
+ * tests/test_kernels_gpu.py) and against golden fixtures generated from that
  * run (tests/golden/).
  *
  * Arithmetic notes (all verified in the PTX nvcc 12.9 emits for the reference file):

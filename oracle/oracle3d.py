@@ -12,7 +12,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 this module.  The product (gpufluidsimulation_b200) never does.
 
 Parity status: the reference has no tests or golden vectors; this oracle is pinned against the
-reference's own CUDA kernels executed on a B200 (tests/test_ref_kernels_gpu.py, oracle/_ref/libref3d.so).
+reference's own CUDA kernels executed on a B200 (tests/test_kernels_gpu.py, oracle/_ref/libref3d.so).
 """
 from __future__ import annotations
 
