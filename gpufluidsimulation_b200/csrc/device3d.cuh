@@ -231,6 +231,46 @@ __device__ __forceinline__ float3 trace(const Vel3 &vel, const Grid3 &g, float c
     return p;
 }
 
+// N independent particles traced in lock-step: the sub-step sequence depends only on (cfldt, dt),
+// so the RK3 stages of the particles are interleaved inside one loop, which keeps N times as many
+// velocity gathers in flight as tracing them one after the other (same arithmetic per particle).
+template <bool P2, int N>
+__device__ __forceinline__ void trace_multi(const Vel3 &vel, const Grid3 &g, float cfldt, float dt, float3 (&p)[N])
+{
+    const float sgn = dt > 0.f ? 1.0f : -1.0f;
+    const float T = fabsf(dt);
+    float t = 0.f, sub = cfldt;
+    while (t < T) {
+        if (t + sub > T) sub = T - t;
+        const float h_ = sgn * sub;
+        const float c1 = (float)(2.0 / 9.0 * (double)h_), c2 = (float)(3.0 / 9.0 * (double)h_), c3 = (float)(4.0 / 9.0 * (double)h_);
+        const float hd = 0.5f * h_;
+        const double qd = 0.75 * (double)h_;
+        float3 v1[N], v2[N], v3[N];
+#pragma unroll
+        for (int m = 0; m < N; ++m) v1[m] = get_velocity<P2>(vel, g, p[m].x, p[m].y, p[m].z);
+#pragma unroll
+        for (int m = 0; m < N; ++m)
+            v2[m] = get_velocity<P2>(vel, g, fmaf(hd, v1[m].x, p[m].x), fmaf(hd, v1[m].y, p[m].y), fmaf(hd, v1[m].z, p[m].z));
+#pragma unroll
+        for (int m = 0; m < N; ++m)
+            v3[m] = get_velocity<P2>(vel, g, __double2float_rn(__fma_rn(qd, (double)v2[m].x, (double)p[m].x)),
+                                     __double2float_rn(__fma_rn(qd, (double)v2[m].y, (double)p[m].y)),
+                                     __double2float_rn(__fma_rn(qd, (double)v2[m].z, (double)p[m].z)));
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            float3 o;
+            o.x = fmaf(c3, v3[m].x, fmaf(c2, v2[m].x, fmaf(c1, v1[m].x, p[m].x)));
+            o.y = fmaf(c3, v3[m].y, fmaf(c2, v2[m].y, fmaf(c1, v1[m].y, p[m].y)));
+            o.z = fmaf(c3, v3[m].z, fmaf(c2, v2[m].z, fmaf(c1, v1[m].z, p[m].z)));
+            p[m].x = clampf(o.x, g.h, (float)g.ni * g.h - g.h);
+            p[m].y = clampf(o.y, g.h, (float)g.nj * g.h - g.h);
+            p[m].z = clampf(o.z, g.h, (float)g.nk * g.h - g.h);
+        }
+        t += sub;
+    }
+}
+
 // Three co-located map components sampled at one world position (the maps are cell-centred
 // arrays of the global grid with origin 0): one split, 24 loads.
 struct Map3 {

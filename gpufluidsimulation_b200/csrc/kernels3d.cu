@@ -65,13 +65,15 @@ k_forward(Grid3 g, int kbeg, int kend_, Vel3 vel, MapSetRW<NMAP> maps, float cfl
     BMQ_IJK(g.ni, g.nj)
     if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
     const int idx = i + g.ni * (j + g.nj * k);
+    float3 p[NMAP];
+#pragma unroll
+    for (int m = 0; m < NMAP; ++m) p[m] = make_float3(maps.x[m][idx], maps.y[m][idx], maps.z[m][idx]);
+    trace_multi<P2, NMAP>(vel, g, cfldt, dt, p);
 #pragma unroll
     for (int m = 0; m < NMAP; ++m) {
-        float3 p = make_float3(maps.x[m][idx], maps.y[m][idx], maps.z[m][idx]);
-        p = trace<P2>(vel, g, cfldt, dt, p);
-        maps.x[m][idx] = p.x;
-        maps.y[m][idx] = p.y;
-        maps.z[m][idx] = p.z;
+        maps.x[m][idx] = p[m].x;
+        maps.y[m][idx] = p[m].y;
+        maps.z[m][idx] = p[m].z;
     }
 }
 
