@@ -290,7 +290,7 @@ def run_gpu(args):
             "config": {"workload": f"BiMocq3D smoke plume {n}^3 (velocity + density + temperature), maps + 3 velocity "
                                    "components + 2 scalars per step",
                        "grid": [n, n, n], "dt": DT, "cfl_frame": CFL, "n_sub_mean": n_sub, "blend_coeff": 1.0,
-                       "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo {args.halo}, exchange={args.transport}",
+                       "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo {args.halo}, exchange={solver.transport}",
                        "l2_policy": "inputs larger than L2 (537 MB per field vs 126 MB L2), no flush needed"},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         }

@@ -47,6 +47,10 @@ class HaloTooNarrow(RuntimeError):
     pass
 
 
+class PeerUnavailable(RuntimeError):
+    pass
+
+
 def slab_bounds(nk: int, world: int, rank: int):
     """Owned planes [k0, k1) of rank `rank`: contiguous, sizes differ by at most one."""
     base, rem = divmod(nk, world)
@@ -170,31 +174,46 @@ class PeerComm(DistComm):
         self.lib = slab_rank.solver.lib
         self.copy_stream = torch.cuda.Stream(device=device)
         self.flag = torch.zeros(1, dtype=torch.float32, device=device)
-        from .capi import check
+        from .capi import BimocqLibraryError, check
         n = len(self.ALLOC_NAMES)
         handles = torch.zeros((n, 64), dtype=torch.uint8)
         self.index_of_ptr = {}
-        for i, name in enumerate(self.ALLOC_NAMES):
-            ptr = slab_rank.solver.field_info(name)[0]
-            buf = (C.c_ubyte * 64)()
-            check(self.lib.bmq_ipc_export(C.c_void_p(ptr), buf), "bmq_ipc_export")
-            handles[i] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
-            self.index_of_ptr[ptr] = i
+        self.peer = {}
+        ok = 1.0
+        # every rank takes part in every collective below even if a local step failed, and the
+        # outcome is agreed on with a MIN all-reduce, so that either all ranks use peer copies or
+        # all of them raise PeerUnavailable (the caller then falls back to NCCL send/recv)
+        try:
+            for i, name in enumerate(self.ALLOC_NAMES):
+                ptr = slab_rank.solver.field_info(name)[0]
+                buf = (C.c_ubyte * 64)()
+                check(self.lib.bmq_ipc_export(C.c_void_p(ptr), buf), "bmq_ipc_export")
+                handles[i] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+                self.index_of_ptr[ptr] = i
+        except BimocqLibraryError:
+            ok = 0.0
         mine = handles.to(device)
         everyone = [torch.zeros_like(mine) for _ in range(world)]
         self.dist.all_gather(everyone, mine)
         gathered = [g.cpu() for g in everyone]
-        self.peer = {}
-        for nb in (rank - 1, rank + 1):
-            if 0 <= nb < world:
-                ptrs = []
-                for i in range(n):
-                    raw = (C.c_ubyte * 64).from_buffer_copy(bytes(gathered[nb][i].tolist()))
-                    out = C.c_void_p()
-                    check(self.lib.bmq_ipc_open(raw, C.byref(out)), "bmq_ipc_open")   # lazy peer access
-                    ptrs.append(out.value)
-                self.peer[nb] = ptrs
-        self.dist.barrier()
+        try:
+            for nb in (rank - 1, rank + 1):
+                if 0 <= nb < world and ok:
+                    ptrs = []
+                    self.peer[nb] = ptrs
+                    for i in range(n):
+                        raw = (C.c_ubyte * 64).from_buffer_copy(bytes(gathered[nb][i].tolist()))
+                        out = C.c_void_p()
+                        check(self.lib.bmq_ipc_open(raw, C.byref(out)), "bmq_ipc_open")   # lazy peer access
+                        ptrs.append(out.value)
+        except BimocqLibraryError:
+            ok = 0.0
+        agreed = torch.tensor([ok], dtype=torch.float32, device=device)
+        self.dist.all_reduce(agreed, op=self.dist.ReduceOp.MIN)
+        if float(agreed.item()) < 1.0:
+            self.close()
+            self.lib.bmq_clear_error()
+            raise PeerUnavailable("CUDA IPC peer mapping failed on at least one rank")
 
     @staticmethod
     def _check(status, what):
@@ -240,7 +259,8 @@ class PeerComm(DistComm):
     def close(self):
         for ptrs in self.peer.values():
             for p in ptrs:
-                self.lib.bmq_ipc_close(C.c_void_p(p))
+                if p:
+                    self.lib.bmq_ipc_close(C.c_void_p(p))
         self.peer = {}
 
 
@@ -454,15 +474,26 @@ class ZSlabStepper:
 # ----------------------------------------------------------------------------------------------
 class ZSlabAdvection3D:
     def __init__(self, ni, nj, nk, h, blend_coeff=1.0, rank=0, world=1, halo=24, transport="peer"):
-        """transport: "peer" = direct P2P copies of peer-mapped memory over NVLink (PeerComm),
-        "nccl" = NCCL send/recv (DistComm)."""
+        """transport: "peer" = direct P2P copies of peer-mapped memory over NVLink (PeerComm; if the
+        peer mapping cannot be set up on every rank, all ranks fall back to NCCL and say so on
+        stderr), "nccl" = NCCL send/recv (DistComm)."""
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
         self.r = CudaSlabRank(ni, nj, nk, h, blend_coeff, rank, world, halo)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.comm = PeerComm(world, rank, dev, self.r) if transport == "peer" else DistComm(world, rank, dev)
         self.transport = transport
+        if transport == "peer":
+            try:
+                self.comm = PeerComm(world, rank, dev, self.r)
+            except PeerUnavailable as exc:
+                import sys
+                if rank == 0:
+                    print(f"zslab: {exc}; using NCCL send/recv for the halo exchange", file=sys.stderr)
+                self.comm = DistComm(world, rank, dev)
+                self.transport = "nccl"
+        else:
+            self.comm = DistComm(world, rank, dev)
         self.stepper = ZSlabStepper([self.r], self.comm, blend_coeff)
         self.lib = self.r.solver.lib
 
