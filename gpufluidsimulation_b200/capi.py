@@ -115,6 +115,10 @@ _PROTOS = {
     "gpu_compensate_field": (None, [_F] * 9 + [_f, _I, _I, _I, C.c_bool]),
     "gpu_semilag": (None, [_F] * 5 + [_I, _I, _I, _f, _I, _I, _I, _f, _f]),
     "gpu_add_field": (None, [_F, _F, _F, _f, _I]),
+    "gpu_emit_smoke": (None, [_F] * 5 + [_f, _I, _I, _I] + [_f] * 7),
+    "gpu_add_buoyancy": (None, [_F] * 3 + [_I, _I, _I, _f, _f, _f]),
+    "gpu_diffuse_field": (None, [_F] * 3 + [_I, _I, _I, _I, _f]),
+    "gpu_mad": (None, [_F] * 3 + [_f, _f, _I]),
     "bmq3d_create": (_I, [_I, _I, _I, _f, _f, C.POINTER(_H)]),
     "bmq3d_create_slab": (_I, [_I, _I, _I, _f, _f, _I, _I, _I, C.POINTER(_H)]),
     "bmq3d_destroy": (_I, [_H]),

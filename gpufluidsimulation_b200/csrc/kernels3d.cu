@@ -536,17 +536,42 @@ k_maxabs3(const float *__restrict__ a, size_t na, const float *__restrict__ b, s
 }
 
 // a[i] += c*b[i]  (add_kernel, GPU_kernel.cu:560-565, with the missing bounds check) and
-// out[i] = a[i] + c*b[i] (add_field_kernel, :878-883)
-__global__ void __launch_bounds__(256) k_axpy(float *a, const float *__restrict__ b, float c, size_t n)
-{
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) a[e] = fmaf(c, b[e], a[e]);
-}
+// out[i] = a[i] + c*b[i] (add_field_kernel, :878-883).  Streaming: 128-bit loads/stores when the
+// three pointers are 16-byte aligned (always true for whole fields), scalar tail.
+__device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 __global__ void __launch_bounds__(256)
-k_add_field(float *out, const float *__restrict__ a, const float *__restrict__ b, float c, size_t n)
+k_add_field(float *out, const float *a, const float *b, float c, size_t n)
 {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) out[e] = fmaf(c, b[e], a[e]);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if (aligned16(out) && aligned16(a) && aligned16(b)) {
+        const size_t n4 = n / 4;
+        const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b);
+        float4 *o4 = reinterpret_cast<float4 *>(out);
+        for (size_t e = tid; e < n4; e += stride) {
+            const float4 x = a4[e], y = b4[e];
+            o4[e] = make_float4(fmaf(c, y.x, x.x), fmaf(c, y.y, x.y), fmaf(c, y.z, x.z), fmaf(c, y.w, x.w));
+        }
+        done = n4 * 4;
+    }
+    for (size_t e = done + tid; e < n; e += stride) out[e] = fmaf(c, b[e], a[e]);
+}
+__global__ void __launch_bounds__(256) k_axpy(float *a, const float *b, float c, size_t n)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if (aligned16(a) && aligned16(b)) {
+        const size_t n4 = n / 4;
+        const float4 *b4 = reinterpret_cast<const float4 *>(b);
+        float4 *a4 = reinterpret_cast<float4 *>(a);
+        for (size_t e = tid; e < n4; e += stride) {
+            const float4 x = a4[e], y = b4[e];
+            a4[e] = make_float4(fmaf(c, y.x, x.x), fmaf(c, y.y, x.y), fmaf(c, y.z, x.z), fmaf(c, y.w, x.w));
+        }
+        done = n4 * 4;
+    }
+    for (size_t e = done + tid; e < n; e += stride) a[e] = fmaf(c, b[e], a[e]);
 }
 
 // identity maps x = i*h (Mapping.cpp:310-324) for up to two mappers x (psi, chi)

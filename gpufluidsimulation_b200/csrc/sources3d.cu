@@ -1,0 +1,154 @@
+// Source terms around the advection path: smoke emitter, buoyancy,
+// Jacobi diffusion and the mad helper -- the reference's `extern "C"` gpu_emit_smoke,
+// gpu_add_buoyancy, gpu_diffuse_field, gpu_mad (bimocq3D/GPU_Advection.h:88-95,103; definitions
+// bimocq3D/GPU_kernel.cu:736-876, 952-964) with the same prototypes, on the legacy default stream.
+//
+// All four are streaming / 7-point-stencil kernels bounded by HBM bandwidth.  The arithmetic
+// expressions are the reference's (same float/double promotions, same CUDA math functions), so
+// the toolchain makes the same contraction choices and the results are bit-identical.
+#include "common.h"
+#include "launch3d.h"
+
+namespace {
+
+#define SRC_IJK(fi, fj, fk)                                       \
+    const int i = blockIdx.x * 32 + threadIdx.x;                  \
+    const int j = blockIdx.y * 4 + threadIdx.y;                   \
+    const int k = blockIdx.z;                                     \
+    if (i >= (fi) || j >= (fj) || k >= (fk)) return;              \
+    const int index = i + (fi) * (j + (fj) * k);
+
+dim3 sblk() { return dim3(32, 4, 1); }
+dim3 sgrd(int fi, int fj, int fk) { return dim3((fi + 31) / 32, (fj + 3) / 4, fk); }
+
+// emit_smoke_velocity_kernel, GPU_kernel.cu:736-758 (ni,nj,nk are the FIELD's dimensions)
+__global__ void __launch_bounds__(128)
+k_emit_velocity(float *field, float h, int ni, int nj, int nk, float cx, float cy, float cz, float radius, float emiter)
+{
+    SRC_IJK(ni, nj, nk)
+    if (!(i > 1 && i < ni - 2 && j > 1 && j < nj - 2 && k > 1 && k < nk - 2)) return;
+    // written like the reference source (mixed double/float literals included) so that nvcc and
+    // ptxas make the same promotion and contraction choices: the result is bit-identical
+    const float dx = ((float)i - 0.5) * h - cx;
+    const float dy = j * h - cy;
+    const float dz = k * h - cz;
+    const float length = norm3df(dx, dy, dz);
+    if (length < radius) {
+        const float theta = acosf(dy / hypotf(dy, dz));
+        const float vel_x = emiter * 0.06 * (1.0 + 0.01 * cosf(8.0 * theta));
+        field[index] = vel_x;
+    }
+}
+
+// emit_smoke_field_kernel, GPU_kernel.cu:760-780
+__global__ void __launch_bounds__(128)
+k_emit_field(float *rho, float *T, float h, int ni, int nj, int nk, float cx, float cy, float cz, float radius,
+             float density, float temperature)
+{
+    SRC_IJK(ni, nj, nk)
+    if (!(i > 1 && i < ni - 2 && j > 1 && j < nj - 2 && k > 1 && k < nk - 2)) return;
+    const float dx = i * h - cx, dy = j * h - cy, dz = k * h - cz;
+    if (norm3df(dx, dy, dz) < radius) {
+        rho[index] = density;
+        T[index] = temperature;
+    }
+}
+
+// add_buoyancy_kernel, GPU_kernel.cu:804-823: v(i,j,k) += 0.5 dt (beta (T_j + T_{j-1}) - alpha (rho_j + rho_{j-1})).
+// The reference indexes density/temperature with the v-face index (nj+1 rows per plane), i.e. with
+// the v-field's row pitch; that addressing is reproduced (it is what the reference computes).
+__global__ void __launch_bounds__(128)
+k_add_buoyancy(float *field, const float *__restrict__ density, const float *__restrict__ temperature, int ni, int nj,
+               int nk, float alpha, float beta, float dt)
+{
+    SRC_IJK(ni, nj, nk)
+    if (!(j > 0)) return;
+    const int index1 = index - ni;
+    const float d0 = density[index], T0 = temperature[index];
+    const float d1 = density[index1], T1 = temperature[index1];
+    const float f = 0.5 * dt * (beta * (T0 + T1) - alpha * (d0 + d1));   // the reference's expression, same contraction
+    field[index] += f;
+}
+
+// diffuse_field_kernel, GPU_kernel.cu:834-853: one Jacobi sweep of (I - coef Lap) x = field
+__global__ void __launch_bounds__(128)
+k_diffuse(const float *__restrict__ field, const float *__restrict__ in, float *out, int ni, int nj, int nk, float coef)
+{
+    SRC_IJK(ni, nj, nk)
+    if (!(i > 0 && i < ni - 1 && j > 0 && j < nj - 1 && k > 0 && k < nk - 1)) return;
+    const int sy = ni, sz = ni * nj;
+    float s = __fadd_rn(__ldg(in + index - 1), __ldg(in + index + 1));
+    s = __fadd_rn(s, __ldg(in + index - sy));
+    s = __fadd_rn(s, __ldg(in + index + sy));
+    s = __fadd_rn(s, __ldg(in + index - sz));
+    s = __fadd_rn(s, __ldg(in + index + sz));
+    out[index] = __fdiv_rn(__fmaf_rn(coef, s, __ldg(field + index)), __fmaf_rn(coef, 6.0f, 1.0f));
+}
+
+// mad_kernel, GPU_kernel.cu:952-957 (with the bounds check the reference lacks); 128-bit accesses
+// when the pointers allow it
+__global__ void __launch_bounds__(256)
+k_mad(float *field, const float *f1, const float *f2, float c1, float c2, size_t n)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if (((reinterpret_cast<uintptr_t>(field) | reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2)) & 15) == 0) {
+        const size_t n4 = n / 4;
+        const float4 *a4 = reinterpret_cast<const float4 *>(f1), *b4 = reinterpret_cast<const float4 *>(f2);
+        float4 *o4 = reinterpret_cast<float4 *>(field);
+        for (size_t e = tid; e < n4; e += stride) {
+            const float4 x = a4[e], y = b4[e];
+            o4[e] = make_float4(__fmaf_rn(c1, x.x, __fmul_rn(c2, y.x)), __fmaf_rn(c1, x.y, __fmul_rn(c2, y.y)),
+                                __fmaf_rn(c1, x.z, __fmul_rn(c2, y.z)), __fmaf_rn(c1, x.w, __fmul_rn(c2, y.w)));
+        }
+        done = n4 * 4;
+    }
+    for (size_t e = done + tid; e < n; e += stride) field[e] = __fmaf_rn(c1, f1[e], __fmul_rn(c2, f2[e]));
+}
+
+}  // namespace
+
+extern "C" {
+
+void gpu_emit_smoke(float *u, float *v, float *w, float *rho, float *T, float h, int ni, int nj, int nk, float centerX,
+                    float centerY, float centerZ, float radius, float density, float temperature, float emiter)
+{
+    if (!bmq::require_device()) return;
+    k_emit_velocity<<<sgrd(ni + 1, nj, nk), sblk()>>>(u, h, ni + 1, nj, nk, centerX, centerY, centerZ, radius, emiter);
+    k_emit_velocity<<<sgrd(ni, nj + 1, nk), sblk()>>>(v, h, ni, nj + 1, nk, centerX, centerY, centerZ, radius, 0.f);
+    k_emit_velocity<<<sgrd(ni, nj, nk + 1), sblk()>>>(w, h, ni, nj, nk + 1, centerX, centerY, centerZ, radius, 0.f);
+    k_emit_field<<<sgrd(ni, nj, nk), sblk()>>>(rho, T, h, ni, nj, nk, centerX, centerY, centerZ, radius, density, temperature);
+    BMQ_CKV(cudaGetLastError());
+}
+
+void gpu_add_buoyancy(float *field, float *density, float *temperature, int ni, int nj, int nk, float alpha, float beta, float dt)
+{
+    if (!bmq::require_device()) return;
+    k_add_buoyancy<<<sgrd(ni, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt);
+    BMQ_CKV(cudaGetLastError());
+}
+
+void gpu_diffuse_field(float *field, float *fieldTemp0, float *fieldTemp1, int ni, int nj, int nk, int iter, float coef)
+{
+    if (!bmq::require_device()) return;
+    const size_t bytes = sizeof(float) * (size_t)ni * nj * nk;
+    float *in = fieldTemp0, *out = fieldTemp1;
+    BMQ_CKV(cudaMemcpyAsync(in, field, bytes, cudaMemcpyDeviceToDevice, 0));
+    for (int it = 0; it < iter; ++it) {
+        k_diffuse<<<sgrd(ni, nj, nk), sblk()>>>(field, in, out, ni, nj, nk, coef);
+        float *t = out; out = in; in = t;
+    }
+    BMQ_CKV(cudaGetLastError());
+    BMQ_CKV(cudaMemcpyAsync(field, out, bytes, cudaMemcpyDeviceToDevice, 0));
+}
+
+void gpu_mad(float *field, float *field1, float *field2, float coeff1, float coeff2, int number)
+{
+    if (!bmq::require_device() || number <= 0) return;
+    size_t blocks = ((size_t)number / 4 + 255) / 256 + 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_mad<<<(unsigned)blocks, 256>>>(field, field1, field2, coeff1, coeff2, (size_t)number);
+    BMQ_CKV(cudaGetLastError());
+}
+
+}  // extern "C"

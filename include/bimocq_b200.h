@@ -111,6 +111,23 @@ void gpu_semilag(float *field, float *field_src, float *u, float *v, float *w, i
 /* replaces GPU_Advection.h:97 (def. GPU_kernel.cu:885-890): out = field1 + coeff*field2 */
 void gpu_add_field(float *out, float *field1, float *field2, float coeff, int number);
 
+/* ---- source terms on either side of the advection path, same prototypes as
+ * the reference; the Poisson solvers (gpu_projection_jacobi, gpu_conjugate_gradient,
+ * gpu_multi_grid_conjugate_gradient) and the MacCormack clamp (gpu_clamp_extrema) are not provided. */
+/* replaces GPU_Advection.h:88-90 (def. GPU_kernel.cu:782-802) */
+void gpu_emit_smoke(float *u, float *v, float *w, float *rho, float *T, float h, int ni, int nj, int nk,
+                    float centerX, float centerY, float centerZ, float radius, float density,
+                    float temperature, float emiter);
+/* replaces GPU_Advection.h:92-93 (def. GPU_kernel.cu:825-832) */
+void gpu_add_buoyancy(float *field, float *density, float *temperature, int ni, int nj, int nk,
+                      float alpha, float beta, float dt);
+/* replaces GPU_Advection.h:95 (def. GPU_kernel.cu:855-876): `iter` Jacobi sweeps between the two
+ * scratch buffers, then the same buffer the reference copies back (:875) is copied into `field` */
+void gpu_diffuse_field(float *field, float *fieldTemp0, float *filedTemp1, int ni, int nj, int nk,
+                       int iter, float coef);
+/* replaces GPU_Advection.h:103 (def. GPU_kernel.cu:959-964): field = coeff1*field1 + coeff2*field2 */
+void gpu_mad(float *field, float *field1, float *field2, float coeff1, float coeff2, int number);
+
 /* ------------------------------------------------------------------ handle API (3D) */
 typedef struct bmq3d_solver bmq3d_solver;
 

@@ -431,3 +431,78 @@ float o3_max_dist(const float *dist, const signed char *boundary, int ni, int nj
         if ((!boundary || boundary[i] != 2) && dist[i] > m) m = dist[i];
     return sqrtf(m);
 }
+
+/* ---- source terms, GPU_kernel.cu:736-876, 952-964 ------------------- */
+
+/* emit_smoke_velocity_kernel, :736-758; ni,nj,nk are the field's dimensions */
+void o3_emit_velocity(float *field, float h, int ni, int nj, int nk, float cx, float cy, float cz, float radius,
+                      float emiter)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nk; k++)
+        for (int j = 0; j < nj; j++)
+            for (int i = 0; i < ni; i++) {
+                if (!(i > 1 && i < ni - 2 && j > 1 && j < nj - 2 && k > 1 && k < nk - 2)) continue;
+                float dx = (float)(((double)(float)i - 0.5) * (double)h - (double)cx);
+                float dy = (float)j * h - cy, dz = (float)k * h - cz;
+                float length = sqrtf(dx * dx + dy * dy + dz * dz);
+                if (length < radius) {
+                    float theta = acosf(dy / hypotf(dy, dz));
+                    field[IDX3(i, j, k, ni, nj)] =
+                        (float)((double)emiter * 0.06 * (1.0 + 0.01 * (double)cosf(8.0f * theta)));
+                }
+            }
+}
+
+/* emit_smoke_field_kernel, :760-780 */
+void o3_emit_field(float *rho, float *T, float h, int ni, int nj, int nk, float cx, float cy, float cz, float radius,
+                   float density, float temperature)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nk; k++)
+        for (int j = 0; j < nj; j++)
+            for (int i = 0; i < ni; i++) {
+                if (!(i > 1 && i < ni - 2 && j > 1 && j < nj - 2 && k > 1 && k < nk - 2)) continue;
+                float dx = (float)i * h - cx, dy = (float)j * h - cy, dz = (float)k * h - cz;
+                if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+                    rho[IDX3(i, j, k, ni, nj)] = density;
+                    T[IDX3(i, j, k, ni, nj)] = temperature;
+                }
+            }
+}
+
+/* add_buoyancy_kernel, :804-823, launched with nj+1 rows (:831): density/temperature are indexed
+ * with the v-face index, exactly like the reference */
+void o3_add_buoyancy(float *field, const float *density, const float *temperature, int ni, int njp1, int nk,
+                     float alpha, float beta, float dt)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nk; k++)
+        for (int j = 1; j < njp1; j++)
+            for (int i = 0; i < ni; i++) {
+                ptrdiff_t idx = IDX3(i, j, k, ni, njp1), idx1 = idx - ni;
+                float inner = beta * (temperature[idx] + temperature[idx1]) - alpha * (density[idx] + density[idx1]);
+                field[idx] += (float)(0.5 * (double)dt * (double)inner);
+            }
+}
+
+/* diffuse_field_kernel, :834-853: one sweep */
+void o3_diffuse_sweep(const float *field, const float *in, float *out, int ni, int nj, int nk, float coef)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k < nk - 1; k++)
+        for (int j = 1; j < nj - 1; j++)
+            for (int i = 1; i < ni - 1; i++) {
+                ptrdiff_t q = IDX3(i, j, k, ni, nj), sy = ni, sz = (ptrdiff_t)ni * nj;
+                float s = in[q - 1] + in[q + 1];
+                s += in[q - sy]; s += in[q + sy]; s += in[q - sz]; s += in[q + sz];
+                out[q] = fmaf(coef, s, field[q]) / fmaf(coef, 6.0f, 1.0f);
+            }
+}
+
+/* mad_kernel, :952-957 */
+void o3_mad(float *field, const float *f1, const float *f2, float c1, float c2, long n)
+{
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; i++) field[i] = fmaf(c1, f1[i], c2 * f2[i]);
+}

@@ -64,6 +64,11 @@ def lib():
         L.o3_maxabs.restype = f
         L.o3_max_dist.argtypes = [_F, C.c_void_p, i, i, i]
         L.o3_max_dist.restype = f
+        L.o3_emit_velocity.argtypes = [_F, f, i, i, i, f, f, f, f, f]
+        L.o3_emit_field.argtypes = [_F, _F, f, i, i, i, f, f, f, f, f, f]
+        L.o3_add_buoyancy.argtypes = [_F, _F, _F, i, i, i, f, f, f]
+        L.o3_diffuse_sweep.argtypes = [_F, _F, _F, i, i, i, f]
+        L.o3_mad.argtypes = [_F, _F, _F, f, f, C.c_long]
         _LIB = L
     return _LIB
 
@@ -188,6 +193,33 @@ def max_dist(dist, boundary=None):
 
 def maxabs(a, start=0.0):
     return float(lib().o3_maxabs(_p(a), a.size, start))
+
+
+# ---- source terms (GPU_kernel.cu:736-876, 952-964) -----------------------------------------
+def gpu_emit_smoke(u, v, w, rho, T, h, ni, nj, nk, cx, cy, cz, radius, density, temperature, emiter):
+    L = lib()
+    L.o3_emit_velocity(_p(u), h, ni + 1, nj, nk, cx, cy, cz, radius, emiter)
+    L.o3_emit_velocity(_p(v), h, ni, nj + 1, nk, cx, cy, cz, radius, 0.0)
+    L.o3_emit_velocity(_p(w), h, ni, nj, nk + 1, cx, cy, cz, radius, 0.0)
+    L.o3_emit_field(_p(rho), _p(T), h, ni, nj, nk, cx, cy, cz, radius, density, temperature)
+
+
+def gpu_add_buoyancy(field, density, temperature, ni, nj, nk, alpha, beta, dt):
+    lib().o3_add_buoyancy(_p(field), _p(density), _p(temperature), ni, nj + 1, nk, alpha, beta, dt)
+
+
+def gpu_diffuse_field(field, tmp0, tmp1, ni, nj, nk, iters, coef):
+    """gpu_diffuse_field, GPU_kernel.cu:855-876, including which buffer is copied back (:875)."""
+    a, b = tmp0, tmp1
+    a[...] = field
+    for _ in range(iters):
+        lib().o3_diffuse_sweep(_p(field), _p(a), _p(b), ni, nj, nk, coef)
+        a, b = b, a
+    field[...] = b
+
+
+def gpu_mad(field, f1, f2, c1, c2):
+    lib().o3_mad(_p(field), _p(f1), _p(f2), c1, c2, field.size)
 
 
 def identity_maps(ni, nj, nk, h):

@@ -38,6 +38,12 @@ def calls(c):
         "gpu_advect_vel_double": ([f["u"], f["v"], f["w"], g["u"], g["v"], g["w"], *c.bwd, *c.bwd_prev, c.h, c.ni, c.nj, c.nk, False, 0.5], [0, 1, 2]),
         "gpu_advect_field_double": ([f["c"], g["c"], *c.bwd, *c.bwd_prev, c.h, c.ni, c.nj, c.nk, False, 0.25], [0]),
         "gpu_estimate_distortion": ([z(f["c"]), *c.bwd, *c.fwd, c.h, c.ni, c.nj, c.nk], [0]),
+        # source terms
+        "gpu_emit_smoke": ([f["u"], f["v"], f["w"], f["c"], g["c"], c.h, c.ni, c.nj, c.nk, 0.45 * c.h * c.ni, 0.4 * c.h * c.nj,
+                            0.5 * c.h * c.nk, 0.22 * c.h * c.ni, 1.0, 50.0, 1.0], [0, 1, 2, 3, 4]),
+        "gpu_add_buoyancy": ([f["v"], f["c"], g["c"], c.ni, c.nj, c.nk, 0.3, 0.7, 0.02], [0]),
+        "gpu_diffuse_field": ([f["c"], z(f["c"]), z(f["c"]), c.ni, c.nj, c.nk, 4, 0.37], [0]),
+        "gpu_mad": ([z(f["u"]), f["u"], g["u"], 0.75, -1.25, int(f["u"].size)], [0]),
     }
 
 

@@ -31,6 +31,10 @@ def setup(oracle):
     return m, c, np.load(GOLD)
 
 
+def f32_(x):
+    return float(np.float32(x))
+
+
 def _run_oracle(o3, name, arrays, c):
     A = [o3.padded_copy(a) for a in arrays]
     d = (c.h, c.ni, c.nj, c.nk)
@@ -62,6 +66,19 @@ def _run_oracle(o3, name, arrays, c):
         o3.double_advect(A[0], A[1], A[2:5], A[5:8], *d, "c", 0.25)
     elif name == "gpu_estimate_distortion":
         o3.estimate(A[0], A[1:4], A[4:7], *d)
+    elif name == "gpu_emit_smoke":
+        f32 = lambda x: float(np.float32(x))
+        o3.gpu_emit_smoke(*A[:5], c.h, c.ni, c.nj, c.nk, f32(0.45 * c.h * c.ni), f32(0.4 * c.h * c.nj), f32(0.5 * c.h * c.nk),
+                          f32(0.22 * c.h * c.ni), 1.0, 50.0, 1.0)
+    elif name == "gpu_add_buoyancy":
+        big = [o3.padded((c.nk, c.nj + 1, c.ni)) for _ in range(2)]   # indexed with the v-face index by the reference
+        for b, src in zip(big, A[1:3]):
+            b.reshape(-1)[:src.size] = src.reshape(-1)
+        o3.gpu_add_buoyancy(A[0], big[0], big[1], c.ni, c.nj, c.nk, f32_(0.3), f32_(0.7), f32_(0.02))
+    elif name == "gpu_diffuse_field":
+        o3.gpu_diffuse_field(A[0], A[1], A[2], c.ni, c.nj, c.nk, 4, f32_(0.37))
+    elif name == "gpu_mad":
+        o3.gpu_mad(A[0], A[1], A[2], 0.75, -1.25)
     else:
         raise KeyError(name)
     return A
@@ -73,6 +90,7 @@ def test_oracle_matches_reference_kernel_golden_vectors(setup, oracle):
     for name, (args, outs) in m.calls(c).items():
         arrays = [a for a in args if isinstance(a, np.ndarray)]
         A = _run_oracle(oracle, name, arrays, c)
+        # DMC: expf ulp amplification; emitter: acosf/cosf/hypotf of glibc vs CUDA
         tol = 5e-4 if name == "gpu_solve_backwardDMC" else 2e-7
         for q in outs:
             want = gold[f"{name}:out{q}"]

@@ -205,3 +205,49 @@ def test_add_and_add_field(case, oracle, ours, ref):
     assert rel_linf(got[0], want) <= 1e-6
     got = run_gpu_symbol(ours, "gpu_add_field", [np.zeros_like(a), a, b, -1.0, n])
     assert np.array_equal(got[0], a - b)
+
+
+# ---- source terms ------------------------------------------------------
+def test_emit_smoke(case, oracle, ours, ref):
+    c = case
+    f = c.fields
+    L = c.h * c.ni
+    args = [f["u"], f["v"], f["w"], f["c"], c.fields2["c"], c.h, c.ni, c.nj, c.nk, 0.45 * L, 0.4 * c.h * c.nj,
+            0.5 * c.h * c.nk, 0.22 * L, 1.0, 50.0, 1.0]
+    # the emitter's angle goes through acosf / cosf / hypotf: CUDA's and glibc's differ in the last ulps
+    _three_way("gpu_emit_smoke", args,
+               lambda a: oracle.gpu_emit_smoke(a[0], a[1], a[2], a[3], a[4], *[float(np.float32(x)) if isinstance(x, float) else x for x in args[5:]]),
+               ours, ref, [0, 1, 2, 3, 4], tol_oracle=1e-6)
+
+
+@pytest.mark.parametrize("alpha,beta", [(0.0, 0.5), (0.3, 0.7)])
+def test_add_buoyancy(case, oracle, ours, ref, alpha, beta):
+    c = case
+    args = [c.fields["v"], c.fields["c"], c.fields2["c"], c.ni, c.nj, c.nk, alpha, beta, 0.02]
+
+    def run(a):
+        # the reference indexes the cell-centred inputs with the v-face index (nj+1 rows): give the oracle room
+        from oracle import oracle3d as o3
+        big = [o3.padded((c.nk, c.nj + 1, c.ni)) for _ in range(2)]
+        for b, src in zip(big, a[1:3]):
+            b.reshape(-1)[:src.size] = src.reshape(-1)
+        oracle.gpu_add_buoyancy(a[0], big[0], big[1], c.ni, c.nj, c.nk, alpha, beta, 0.02)
+
+    _three_way("gpu_add_buoyancy", args, run, ours, ref, [0])
+
+
+@pytest.mark.parametrize("iters", [1, 4])
+def test_diffuse_field(case, oracle, ours, ref, iters):
+    c = case
+    f = c.fields["c"]
+    args = [f, np.zeros_like(f), np.zeros_like(f), c.ni, c.nj, c.nk, iters, 0.37]
+    _three_way("gpu_diffuse_field", args,
+               lambda a: oracle.gpu_diffuse_field(a[0], a[1], a[2], c.ni, c.nj, c.nk, iters, float(np.float32(0.37))),
+               ours, ref, [0])
+
+
+def test_mad(case, oracle, ours, ref):
+    c = case
+    a, b = c.fields["u"], c.fields2["u"]
+    args = [np.zeros_like(a), a, b, 0.75, -1.25, a.size]
+    _three_way("gpu_mad", args, lambda x: oracle.gpu_mad(x[0], x[1], x[2], 0.75, -1.25), ours, ref, [0])

@@ -91,5 +91,30 @@ def main():
         print(json.dumps({"reference_kernels_ms": {k: round(v, 3) for k, v in r.items()}}, indent=1))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--sources" not in sys.argv:
     main()
+
+
+def source_terms(n=512):
+    """GB/s of the streaming source-term symbols (gpu_add_buoyancy, gpu_diffuse_field, gpu_mad)."""
+    from gpufluidsimulation_b200 import load_library
+    from gpufluidsimulation_b200.solver3d import alloc_field
+    lib = load_library()
+    F = C.POINTER(C.c_float)
+    p = lambda t: C.cast(C.c_void_p(t.data_ptr()), F)
+    v = alloc_field((n, n + 1, n)); rho = alloc_field((n + 1, n + 1, n)); T = alloc_field((n + 1, n + 1, n))
+    a = alloc_field((n, n, n)); b = alloc_field((n, n, n)); c = alloc_field((n, n, n))
+    a.normal_(); T.normal_()
+    cells = n ** 3
+    out = {}
+    t = timed(lambda: lib.gpu_add_buoyancy(p(v), p(rho), p(T), n, n, n, 0.1, 0.2, 0.02))
+    out["gpu_add_buoyancy"] = {"ms": t, "alg_GBps": 4 * 4 * cells / t / 1e6}          # R rho,T,v + W v
+    t = timed(lambda: lib.gpu_diffuse_field(p(a), p(b), p(c), n, n, n, 20, 0.1), reps=2)
+    out["gpu_diffuse_field(20 sweeps)"] = {"ms": t, "alg_GBps": (20 * 3 + 4) * 4 * cells / t / 1e6}   # per sweep R field,in + W out
+    t = timed(lambda: lib.gpu_mad(p(c), p(a), p(b), 0.5, 0.25, cells))
+    out["gpu_mad"] = {"ms": t, "alg_GBps": 3 * 4 * cells / t / 1e6}
+    print(json.dumps({"source_terms_512": out}, indent=1))
+
+
+if "--sources" in sys.argv:
+    source_terms()
