@@ -92,6 +92,14 @@ class Stats2D(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CoarseLevel(C.Structure):
+    """bmq_coarse_level == the reference's SCoarseLevelInfo (GPU_Advection.h:13-24)."""
+    _fields_ = [("ni", _I), ("nj", _I), ("nk", _I), ("number", _I), ("alpha", C.c_double), ("beta", C.c_double),
+                ("b", C.c_void_p), ("x", C.c_void_p), ("r", C.c_void_p)]
+
+
+_D = C.c_void_p   # device double*
+
 _PROTOS = {
     "bmq_last_error": (C.c_char_p, []),
     "bmq_clear_error": (_I, []),
@@ -119,6 +127,13 @@ _PROTOS = {
     "gpu_add_buoyancy": (None, [_F] * 3 + [_I, _I, _I, _f, _f, _f]),
     "gpu_diffuse_field": (None, [_F] * 3 + [_I, _I, _I, _I, _f]),
     "gpu_mad": (None, [_F] * 3 + [_f, _f, _I]),
+    "gpu_multi_grid_conjugate_gradient": (None, [_F] * 3 + [_D] * 7 + [C.POINTER(CoarseLevel), _I, _I, C.c_double]),
+    "bmq_mgpcg_create": (_I, [_I, _I, _I, _I, C.POINTER(_H)]),
+    "bmq_mgpcg_destroy": (None, [_H]),
+    "bmq_mgpcg_set_stream": (_I, [_H, C.c_void_p]),
+    "bmq_mgpcg_solve": (_I, [_H, _F, _F, _F, _I, C.c_double]),
+    "bmq_mgpcg_buffer": (_I, [_H, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
+    "bmq_mgpcg_levels": (_I, [_H, C.POINTER(CoarseLevel), _I]),
     "bmq3d_create": (_I, [_I, _I, _I, _f, _f, C.POINTER(_H)]),
     "bmq3d_create_slab": (_I, [_I, _I, _I, _f, _f, _I, _I, _I, C.POINTER(_H)]),
     "bmq3d_destroy": (_I, [_H]),

@@ -17,6 +17,7 @@ namespace bmq {
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long kernel_launch_count() { return g_launches.load(); }
 static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static inline bool is_pow2_h(const Grid3 &g)
 {

@@ -128,6 +128,41 @@ void gpu_diffuse_field(float *field, float *fieldTemp0, float *filedTemp1, int n
 /* replaces GPU_Advection.h:103 (def. GPU_kernel.cu:959-964): field = coeff1*field1 + coeff2*field2 */
 void gpu_mad(float *field, float *field1, float *field2, float coeff1, float coeff2, int number);
 
+/* ------------------------------------------------------------------ pressure projection */
+/* One multigrid level; identical layout to the reference's SCoarseLevelInfo (GPU_Advection.h:13-24),
+ * so a reference-side `SCoarseLevelInfo levels[LEVEL_COUNT]` can be passed as is. */
+typedef struct bmq_coarse_level {
+    int ni, nj, nk;
+    int number;          /* ni*nj*nk */
+    double alpha, beta;  /* Jacobi: x <- (sum of six neighbours + alpha*b) * beta */
+    double *b, *x, *r;   /* device, `number` doubles each */
+} bmq_coarse_level;
+
+/* replaces GPU_Advection.h:107-108 (def. GPU_kernel.cu:1784-1828; called from
+ * BimocqGPUSolver::projection, BimocqGPUSolver.cpp:443-445): `iter` iterations of the reference's
+ * multigrid-corrected CG on  lap p = halfrdx * div(u,v,w), then u,v,w -= halfrdx * grad p.
+ * Outputs bit-identical to the reference: u, v, w, p, div, residual, dir, tempResult[0..2*iter+2]
+ * (CG scalars) and tempResult[2000..2000+iter] (max residual).  temp0, temp1 and levels[].b/x/r are
+ * scratch.  Prolongation on a level whose size is even reads one plane past levels[].x in the
+ * reference (GPU_kernel.cu:1611-1622 with ci = (ni-1)/2); here those reads return 0. */
+void gpu_multi_grid_conjugate_gradient(float *u, float *v, float *w, double *div, double *p, double *dir,
+                                       double *residual, double *temp0, double *temp1, double *tempResult,
+                                       bmq_coarse_level *levels, int levelNum, int iter, double halfrdx);
+
+/* Handle that owns the fp64 work buffers BimocqGPUSolver's constructor allocates
+ * (BimocqGPUSolver.cpp:56-90): div, p, dir, residual, temp0, temp1, tempResult[4096] and `levels`
+ * levels with n_{l+1} = (n_l - 1)/2, alpha = -1, beta = 1/6. */
+typedef struct bmq_mgpcg bmq_mgpcg;
+enum { BMQ_MG_DIV = 0, BMQ_MG_P, BMQ_MG_DIR, BMQ_MG_RESIDUAL, BMQ_MG_RESULT };
+int  bmq_mgpcg_create(int ni, int nj, int nk, int levels, bmq_mgpcg **out);
+void bmq_mgpcg_destroy(bmq_mgpcg *m);
+int  bmq_mgpcg_set_stream(bmq_mgpcg *m, void *cuda_stream);
+/* = BimocqGPUSolver::projection (iter = 50, halfrdx = 0.5 there); u, v, w are device face fields */
+int  bmq_mgpcg_solve(bmq_mgpcg *m, float *u, float *v, float *w, int iter, double halfrdx);
+int  bmq_mgpcg_buffer(bmq_mgpcg *m, int which, double **device_ptr, long long *count);
+/* copies the level table (device pointers inside) to `out`; returns the number of levels */
+int  bmq_mgpcg_levels(bmq_mgpcg *m, bmq_coarse_level *out, int capacity);
+
 /* ------------------------------------------------------------------ handle API (3D) */
 typedef struct bmq3d_solver bmq3d_solver;
 

@@ -31,8 +31,8 @@ _F = C.POINTER(C.c_float)
 def build(force: bool = False) -> str:
     """Compile liboracle3d.so (and oracle/_ref when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle3d.so")
-    src = os.path.join(_HERE, "bimocq3d_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, n) for n in ("bimocq3d_oracle.c", "projection_oracle.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         try:
             subprocess.check_call(["make", "-C", _HERE, "liboracle3d.so"], stdout=subprocess.DEVNULL)
         except (OSError, subprocess.CalledProcessError):
@@ -69,6 +69,9 @@ def lib():
         L.o3_add_buoyancy.argtypes = [_F, _F, _F, i, i, i, f, f, f]
         L.o3_diffuse_sweep.argtypes = [_F, _F, _F, i, i, i, f]
         L.o3_mad.argtypes = [_F, _F, _F, f, f, C.c_long]
+        _D = C.POINTER(C.c_double)
+        L.o3_mgpcg.argtypes = [_F, _F, _F, _D, _D, _D, _D, _D, i, i, i, i, i, C.c_double]
+        L.o3_mgpcg.restype = i
         _LIB = L
     return _LIB
 
@@ -220,6 +223,24 @@ def gpu_diffuse_field(field, tmp0, tmp1, ni, nj, nk, iters, coef):
 
 def gpu_mad(field, f1, f2, c1, c2):
     lib().o3_mad(_p(field), _p(f1), _p(f2), c1, c2, field.size)
+
+
+def gpu_multi_grid_conjugate_gradient(u, v, w, levels=6, iters=50, halfrdx=0.5, div=None, residual=None, dir=None):
+    """gpu_multi_grid_conjugate_gradient (GPU_kernel.cu:1784-1828) with the level table of
+    BimocqGPUSolver.cpp:68-90.  u, v, w (float32 face fields, shapes (nk,nj,ni+1), (nk,nj+1,ni),
+    (nk+1,nj,ni)) are projected in place; returns dict(p, div, residual, dir, result) of float64."""
+    nk, nj, ni = u.shape[0], u.shape[1], u.shape[2] - 1
+    assert v.shape == (nk, nj + 1, ni) and w.shape == (nk + 1, nj, ni)
+    for a in (u, v, w):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    z = lambda a: np.zeros((nk, nj, ni), np.float64) if a is None else np.ascontiguousarray(a, np.float64)
+    out = dict(p=np.zeros((nk, nj, ni)), div=z(div), residual=z(residual), dir=z(dir), result=np.zeros(4096))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = lib().o3_mgpcg(_p(u), _p(v), _p(w), dp(out["div"]), dp(out["p"]), dp(out["dir"]), dp(out["residual"]),
+                        dp(out["result"]), ni, nj, nk, levels, iters, halfrdx)
+    if rc != 0:
+        raise ValueError(f"o3_mgpcg: {levels} levels do not fit a {ni}x{nj}x{nk} grid")
+    return out
 
 
 def identity_maps(ni, nj, nk, h):

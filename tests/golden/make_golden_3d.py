@@ -4,7 +4,8 @@ oracle/Makefile) on a B200:  gpurun -- python tests/golden/make_golden_3d.py
 The file holds, for every hot-path extern "C" gpu_* symbol, the seeded inputs and the reference's
 outputs on a 20 x 18 x 22 grid with the reference scene's cell size h = 0.2/ni (non power of two).
 tests/test_golden_cpu.py pins the CPU oracle against it; tests/test_golden_gpu.py pins the CUDA
-library against it."""
+library against it.  Also writes tests/golden/ref3d_projection.npz (pressure projection, see
+projection_golden below); copy both from gpurun_out/ into tests/golden/."""
 import os
 import sys
 
@@ -58,6 +59,22 @@ def main():
             store[f"{name}:out{q}"] = got[q]
     np.savez_compressed(os.path.join(ROOT, "gpurun_out", "ref3d_kernels.npz"), **store)
     print("wrote", len(store), "arrays")
+    projection_golden(lib)
+
+
+PROJECTION_CASE = (24, 20, 28, 2, 4)   # ni, nj, nk, levels, iterations
+
+
+def projection_golden(lib):
+    """tests/golden/ref3d_projection.npz: the reference's gpu_multi_grid_conjugate_gradient on the
+    seeded velocity of tests/test_projection_gpu.py (inputs are regenerated from the seed there)."""
+    from test_projection_gpu import run_legacy
+
+    out = run_legacy(lib, *PROJECTION_CASE)
+    keep = {k: out[k] for k in ("u", "v", "w", "p", "result")}
+    keep["result"] = np.concatenate([out["result"][:16], np.zeros(2000 - 16), out["result"][2000:2016], np.zeros(4096 - 2016)])
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", "ref3d_projection.npz"), case=np.array(PROJECTION_CASE), **keep)
+    print("wrote projection golden", PROJECTION_CASE)
 
 
 if __name__ == "__main__":

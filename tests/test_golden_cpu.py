@@ -98,3 +98,22 @@ def test_oracle_matches_reference_kernel_golden_vectors(setup, oracle):
             assert err <= tol, (name, q, err)
             seen += 1
     assert seen == len(gold.files)
+
+
+def test_projection_oracle_matches_reference_golden(oracle):
+    """oracle/projection_oracle.c against the reference's gpu_multi_grid_conjugate_gradient run on a
+    B200 (tests/golden/ref3d_projection.npz): fp64/fp32 results bit for bit."""
+    path = os.path.join(HERE, "golden", "ref3d_projection.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden projection vectors not generated yet")
+    from test_projection_gpu import velocity
+
+    g = np.load(path)
+    ni, nj, nk, levels, iters = (int(x) for x in g["case"])
+    u, v, w = velocity(ni, nj, nk)
+    out = oracle.gpu_multi_grid_conjugate_gradient(u, v, w, levels=levels, iters=iters, halfrdx=0.5)
+    assert np.array_equal(out["p"], g["p"])
+    for name, a in (("u", u), ("v", v), ("w", w)):
+        assert np.array_equal(a, g[name]), name
+    assert np.array_equal(out["result"][: 2 * iters + 3], g["result"][: 2 * iters + 3])
+    assert np.array_equal(out["result"][2000:2001 + iters], g["result"][2000:2001 + iters])
