@@ -22,7 +22,9 @@
 // instead of K times.  Every cell value is produced by the same fp64 expression from the same
 // operands as in the reference's sweep-by-sweep kernels, hence bit-identical.  The reference's
 // memsets (two level-0-sized ones per level) disappear: the first pass of a smoothing run knows
-// x = 0, and every pass writes the zero Dirichlet ring itself.  Single-CTA reductions of the
+// x = 0, and every pass writes the zero Dirichlet ring itself.  (Tried and rejected on B200: a
+// 2 x 2-cells-per-thread variant with parity-split shared planes -- 24 B instead of 40 B of shared
+// traffic per update but 128 registers, 16 warps/SM and 42 % issue utilisation: 35 % slower.)  Single-CTA reductions of the
 // reference (calc_max over all cells) become grid-wide ones (max is exact in any order).
 #include <algorithm>
 #include <cstdint>
@@ -57,11 +59,14 @@ __device__ __forceinline__ double jacobi_value(double s, double alpha, double b,
 {
     return __dmul_rn(__fma_rn(alpha, b, s), beta);
 }
-// the reference's float lerp (GPU_kernel.cu:22-25) applied to doubles: arguments are rounded to
-// float on the way in, the result on the way out
+// the reference's float lerp (GPU_kernel.cu:22-25), `(1.0-c)*a + c*b` = float product c*b, double
+// fma, rounding to float.  For the fractions that occur here (0 and 1/2) 1-c is exact in fp32, and
+// rounding the exact (1-c)*a + (c*b) once (fmaf) equals rounding it to 53 and then to 24 bits
+// (innocuous double rounding, 53 >= 2*24+2) -- so plain fp32 gives the same bits without the
+// quarter-rate double<->float conversions.
 __device__ __forceinline__ float lerp_f(float a, float b, float c)
 {
-    return __double2float_rn(__fma_rn(__dsub_rn(1.0, (double)c), (double)a, (double)__fmul_rn(c, b)));
+    return __fmaf_rn(__fsub_rn(1.0f, c), a, __fmul_rn(c, b));
 }
 
 #define P3_IJK(fi, fj, fk)                                        \
@@ -134,7 +139,9 @@ k_residual(double *r, const double *__restrict__ b, const double *__restrict__ x
         __syncthreads();
         if (threadIdx.x == 0 && threadIdx.y == 0) {
             m = fmax(fmax(wm[0], wm[1]), fmax(wm[2], wm[3]));
-            if (m > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(m));   // m >= 0: bit order == value order
+            // m >= 0: bit order == value order.  Most CTAs lose against the current maximum: test first
+            if (m > 0.0 && m > __longlong_as_double((long long)*(volatile unsigned long long *)maxbits))
+                atomicMax(maxbits, (unsigned long long)__double_as_longlong(m));
         }
     }
 }
@@ -188,39 +195,46 @@ k_dot(const double *__restrict__ v0, const double *__restrict__ v1, double *out,
     }
 }
 
-// calc_sum<double>, GPU_kernel.cu:1134-1178 (single CTA, 256 sequential chains of `cpt` partials,
-// then the 16 x 16 tree in double)
-__global__ void __launch_bounds__(256) k_sum(const double *__restrict__ v, double *out, int count, int cpt, int slot)
+// calc_sum<double>, GPU_kernel.cu:1134-1178: 256 sequential chains of `cpt` partials, then a
+// 16 x 16 tree in double.  The reference runs it in ONE CTA with strided, uncoalesced reads; here
+// every chain gets its own warp (coalesced 256-byte reads, the 32 values broadcast in order by
+// shuffles so that the adds happen in the reference's order), and a second tiny kernel does the tree.
+__global__ void __launch_bounds__(128) k_sum_chains(const double *__restrict__ v, double *chain_sums, int count, int cpt)
 {
-    __shared__ double s[272];
-    const int t = threadIdx.x;
-    const int beg = t * cpt;
+    const int lane = threadIdx.x & 31, chain = blockIdx.x * 4 + (threadIdx.x >> 5);   // 64 CTAs x 4 warps = 256 chains
+    const long long beg = (long long)chain * cpt;
     double a = 0.0;
-    int q = 0;
-    for (; q + 8 <= cpt && beg + q + 8 <= count; q += 8) {
-        double x[8];
+    double nxt = (lane < cpt && beg + lane < count) ? v[beg + lane] : 0.0;
+    for (int q = 0; q < cpt; q += 32) {
+        const double cur = nxt;
+        const int qn = q + 32 + lane;
+        nxt = (qn < cpt && beg + qn < count) ? v[beg + qn] : 0.0;
+        const int lim = min(32, min(cpt - q, (int)max(0LL, min((long long)count - beg - q, 32LL))));
+        if (lim == 32) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) x[m] = v[beg + q + m];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) a = __dadd_rn(a, x[m]);
+            for (int m = 0; m < 32; ++m) a = __dadd_rn(a, __shfl_sync(0xffffffffu, cur, m));
+        } else {
+            for (int m = 0; m < lim; ++m) a = __dadd_rn(a, __shfl_sync(0xffffffffu, cur, m));
+        }
     }
-    for (; q < cpt; ++q)
-        if (beg + q < count) a = __dadd_rn(a, v[beg + q]);
-    s[t] = a;
-    __syncthreads();
+    if (lane == 0) chain_sums[chain] = a;
+}
+__global__ void __launch_bounds__(32) k_sum_tree(const double *__restrict__ chain_sums, double *out, int slot)
+{
+    const int t = threadIdx.x;
+    double g = 0.0;
     if (t < 16) {
-        double g = s[t * 16];
+        g = chain_sums[t * 16];
 #pragma unroll
-        for (int m = 1; m < 16; ++m) g = __dadd_rn(g, s[t * 16 + m]);
-        s[256 + t] = g;
+        for (int m = 1; m < 16; ++m) g = __dadd_rn(g, chain_sums[t * 16 + m]);
     }
-    __syncthreads();
-    if (t == 0) {
-        double g = s[256];
+    double acc = 0.0;
 #pragma unroll
-        for (int m = 1; m < 16; ++m) g = __dadd_rn(g, s[256 + m]);
-        out[slot] = g;
+    for (int m = 0; m < 16; ++m) {
+        const double gm = __shfl_sync(0xffffffffu, g, m);
+        acc = m == 0 ? gm : __dadd_rn(acc, gm);
     }
+    if (t == 0) out[slot] = acc;
 }
 
 // update_x_kernel(double), GPU_kernel.cu:1291-1298:  x += dir * alpha[r] / alpha[d]
@@ -272,13 +286,25 @@ __global__ void __launch_bounds__(128)
 k_restrict(const double *__restrict__ r, double *coarse, int ni, int nj, int nk, int ci, int cj, int ck)
 {
     P3_IJK(ci, cj, ck)
-    const int number = ni * nj * nk;
+    // the eight samples sit at the centres of the eight 2x2x2 sub-blocks of the fine 3x3x3 block at
+    // (2i, 2j, 2k); all fractions are 1/2.  Load the 27 values once (rounded to float as the
+    // reference's float lerp does on entry); indices stay inside the fine array (2c+2 <= n-1).
+    float f[3][3][3];
+    const double *base = r + (2 * i + (size_t)ni * (2 * j + (size_t)nj * (2 * k)));
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int b_ = 0; b_ < 3; ++b_)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) f[c][b_][a] = __double2float_rn(base[a + (size_t)ni * (b_ + (size_t)nj * c)]);
     double acc = 0.0;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         // value0..7: z varies fastest, then y, then x (:1568-1590)
         const int ox = (m >> 2) & 1, oy = (m >> 1) & 1, oz = m & 1;
-        const float v = tri_f(r, ni, nj, number, 2 * i + ox, 2 * j + oy, 2 * k + oz, 0.5f, 0.5f, 0.5f);
+        const float v = lerp_f(lerp_f(lerp_f(f[oz][oy][ox], f[oz][oy][ox + 1], 0.5f), lerp_f(f[oz][oy + 1][ox], f[oz][oy + 1][ox + 1], 0.5f), 0.5f),
+                               lerp_f(lerp_f(f[oz + 1][oy][ox], f[oz + 1][oy][ox + 1], 0.5f), lerp_f(f[oz + 1][oy + 1][ox], f[oz + 1][oy + 1][ox + 1], 0.5f), 0.5f),
+                               0.5f);
         acc = m == 0 ? (double)v : __dadd_rn(acc, (double)v);
     }
     coarse[index] = __ddiv_rn(acc, 8.0);
@@ -367,7 +393,8 @@ k_jacobi_tb(const double *__restrict__ xin, const double *__restrict__ b, double
 // ---- host side --------------------------------------------------------------------------------
 struct Mg {
     cudaStream_t st;
-    unsigned long long *maxbits;   // device scalar for the max reductions
+    double *scratch;               // device: [0] = bits of the running max, [1..256] = calc_sum chain sums
+    unsigned long long *maxbits;   // == scratch[0]
     int status = BMQ_OK;
 
     void ck(cudaError_t e, const char *what)
@@ -385,8 +412,15 @@ struct Mg {
     {
         constexpr int OX = TX - 2 * K, OY = TY - 2 * K;
         const int tiles = ((ni + OX - 1) / OX) * ((nj + OY - 1) / OY);
-        // enough z-chunks to fill the GPU (one 1024-thread CTA per SM), chunks not shorter than 8 K planes
-        int nz = std::max(1, std::min((2 * 148 + tiles - 1) / tiles, std::max(1, nk / (8 * K))));
+        // z-chunks: one CTA per SM is resident (148 SMs); pick the chunk count that wastes least
+        // between the last partial wave and the K apron planes every chunk re-computes
+        int nz = 1;
+        double best = 0.0;
+        for (int c = 1; c <= std::max(1, nk / (4 * K)); ++c) {
+            const int zc = (nk + c - 1) / c, ctas = tiles * ((nk + zc - 1) / zc);
+            const double eff = (double)ctas / (148.0 * ((ctas + 147) / 148)) * zc / (zc + 2.0 * K);
+            if (eff > best + 1e-9) { best = eff; nz = c; }
+        }
         const int zchunk = (nk + nz - 1) / nz;
         nz = (nk + zchunk - 1) / zchunk;
         dim3 grid((ni + OX - 1) / OX, (nj + OY - 1) / OY, nz), block(TX, TY);
@@ -443,8 +477,9 @@ struct Mg {
     {
         const int nref = (number + 255) / 256, cpt = (nref + 255) / 256;
         k_dot<<<std::min((nref + 7) / 8, 148 * 8), 256, 0, st>>>(v0, v1, partials, number, nref);
-        k_sum<<<1, 256, 0, st>>>(partials, res, nref, cpt, slot);
-        post("k_dot/k_sum", 2);
+        k_sum_chains<<<64, 128, 0, st>>>(partials, scratch + 1, nref, cpt);
+        k_sum_tree<<<1, 32, 0, st>>>(scratch + 1, res, slot);
+        post("k_dot/k_sum", 3);
     }
 
     // V_Cycle(b, x, residual, levels, temp0, tempResult, levelnum, offset), GPU_kernel.cu:1634-1712
@@ -531,7 +566,7 @@ struct bmq_mgpcg {
     std::vector<Lvl> levels;
     std::vector<void *> allocs;
     double *div = nullptr, *p = nullptr, *dir = nullptr, *residual = nullptr, *temp0 = nullptr, *temp1 = nullptr, *result = nullptr;
-    unsigned long long *maxbits = nullptr;
+    double *scratch = nullptr;
     cudaStream_t stream = 0;
 };
 
@@ -546,9 +581,9 @@ void gpu_multi_grid_conjugate_gradient(float *u, float *v, float *w, double *div
         bmq::set_error(BMQ_ERR_ARG, "gpu_multi_grid_conjugate_gradient: bad level table");
         return;
     }
-    static unsigned long long *maxbits = nullptr;   // 8-byte device scalar, allocated once per process
-    if (!maxbits) BMQ_CKV(cudaMalloc(&maxbits, sizeof(*maxbits)));
-    Mg mg{0, maxbits};
+    static double *scratch = nullptr;   // 257 doubles of device scratch, allocated once per process
+    if (!scratch) BMQ_CKV(cudaMalloc(&scratch, 257 * sizeof(double)));
+    Mg mg{0, scratch, reinterpret_cast<unsigned long long *>(scratch)};
     mg.solve(u, v, w, div, p, dir, residual, temp0, temp1, tempResult, levels, levelNum, iter, halfrdx);
 }
 
@@ -592,7 +627,7 @@ int bmq_mgpcg_create(int ni, int nj, int nk, int levels, bmq_mgpcg **out)
     for (double **b : bufs)
         if (st == BMQ_OK) st = alloc(nb, (void **)b);
     if (st == BMQ_OK) st = alloc(sizeof(double) * 4096, (void **)&m->result);
-    if (st == BMQ_OK) st = alloc(sizeof(unsigned long long), (void **)&m->maxbits);
+    if (st == BMQ_OK) st = alloc(257 * sizeof(double), (void **)&m->scratch);
     if (st != BMQ_OK) {
         for (void *a : m->allocs) cudaFree(a);
         delete m;
@@ -620,7 +655,7 @@ int bmq_mgpcg_solve(bmq_mgpcg *m, float *u, float *v, float *w, int iter, double
 {
     if (!m || !u || !v || !w) return bmq::set_error(BMQ_ERR_ARG, "bmq_mgpcg_solve: null argument");
     if (iter < 0 || iter > 1000) return bmq::set_error(BMQ_ERR_ARG, "bmq_mgpcg_solve: iter %d outside [0, 1000]", iter);
-    Mg mg{m->stream, m->maxbits};
+    Mg mg{m->stream, m->scratch, reinterpret_cast<unsigned long long *>(m->scratch)};
     mg.solve(u, v, w, m->div, m->p, m->dir, m->residual, m->temp0, m->temp1, m->result, m->levels.data(), m->nlev, iter, halfrdx);
     return mg.status;
 }
