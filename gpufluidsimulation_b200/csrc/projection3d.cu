@@ -24,7 +24,9 @@
 // memsets (two level-0-sized ones per level) disappear: the first pass of a smoothing run knows
 // x = 0, and every pass writes the zero Dirichlet ring itself.  (Tried and rejected on B200: a
 // 2 x 2-cells-per-thread variant with parity-split shared planes -- 24 B instead of 40 B of shared
-// traffic per update but 128 registers, 16 warps/SM and 42 % issue utilisation: 35 % slower.)  Single-CTA reductions of the
+// traffic per update but 128 registers, 16 warps/SM and 42 % issue utilisation: 35 % slower; two
+// cells per thread at 1024 threads: 34 % slower.  The pass is bound by the per-warp dependency
+// chain LDS -> 5 DADD -> DFMA -> DMUL per level, so it wants many warps, not more work per warp.)  Single-CTA reductions of the
 // reference (calc_max over all cells) become grid-wide ones (max is exact in any order).
 #include <algorithm>
 #include <cstdint>
@@ -350,9 +352,11 @@ k_jacobi_tb(const double *__restrict__ xin, const double *__restrict__ b, double
     for (int e = ty * TX + tx; e < K * 2 * PLANE; e += TX * TY) sm[e] = 0.0;
     __syncthreads();
 
-    double lv0[K], lv1[K], bq[K];   // level t at planes (z-1-t), (z-2-t);  b at planes z-1-t
+    // lv[slot][t]: level t on the last planes; the three slots change roles with the iteration
+    // (the z loop is unrolled 3x so that this is register renaming, not moves).  bq[t]: b on plane z-1-t.
+    double lv[3][K], bq[K];
 #pragma unroll
-    for (int t = 0; t < K; ++t) lv0[t] = lv1[t] = bq[t] = 0.0;
+    for (int t = 0; t < K; ++t) lv[0][t] = lv[1][t] = lv[2][t] = bq[t] = 0.0;
 
     double nx = 0.0, nb = 0.0;
     if (in_dom) {
@@ -360,33 +364,39 @@ k_jacobi_tb(const double *__restrict__ xin, const double *__restrict__ b, double
         nb = b[col + plane * zs];
     }
     double *my = sm + (ty + 1) * PX + (tx + 1);
-    for (int z = zs; z <= ze; ++z) {
-        const int wr = (z - zs) & 1, rd = wr ^ 1;
-        const double cur = nx, curb = nb;
-        nx = 0.0;
-        nb = 0.0;
-        if (in_dom && z + 1 <= ze && z + 1 < nk) {
-            if (!ZERO_IN) nx = xin[col + plane * (z + 1)];
-            nb = b[col + plane * (z + 1)];
-        }
-        double up = cur;   // level t at plane z - t
+    int wro = 0, rdo = PLANE;   // offsets of the write / read halves of the double buffer
+    // iterations past ze (at most two) only produce planes nobody stores
+    for (int zb = zs; zb <= ze; zb += 3) {
 #pragma unroll
-        for (int t = 0; t < K; ++t) {
-            my[(t * 2 + wr) * PLANE] = up;
-            const double *s = my + (t * 2 + rd) * PLANE;   // level t, plane z-1-t
-            const int p = z - 1 - t;
-            const double sum = sum6(s[-1], s[1], s[-PX], s[PX], lv1[t], up);
-            const double val = (in_xy && p > 0 && p < nk - 1) ? jacobi_value(sum, alpha, bq[t], beta) : 0.0;
-            lv1[t] = lv0[t];
-            lv0[t] = up;
-            up = val;
-        }
+        for (int r = 0; r < 3; ++r) {
+            const int z = zb + r;
+            const int NEWS = r, OLD = (r + 1) % 3;   // slot that receives plane z-t; slot holding plane z-2-t
+            double up = nx;   // level t at plane z - t
+            const double curb = nb;
+            nx = 0.0;
+            nb = 0.0;
+            if (in_dom && z + 1 < nk) {
+                if (!ZERO_IN) nx = xin[col + plane * (z + 1)];
+                nb = b[col + plane * (z + 1)];
+            }
 #pragma unroll
-        for (int t = K - 1; t > 0; --t) bq[t] = bq[t - 1];
-        bq[0] = curb;
-        const int po = z - K;
-        if (owner && po >= zc0 && po < zc1) xout[col + plane * po] = up;
-        __syncthreads();
+            for (int t = 0; t < K; ++t) {
+                my[t * 2 * PLANE + wro] = up;
+                const double *s = my + t * 2 * PLANE + rdo;   // level t, plane z-1-t
+                const double sum = sum6(s[-1], s[1], s[-PX], s[PX], lv[OLD][t], up);
+                const int p = z - 1 - t;
+                const double val = (in_xy && p > 0 && p < nk - 1) ? jacobi_value(sum, alpha, bq[t], beta) : 0.0;
+                lv[NEWS][t] = up;
+                up = val;
+            }
+#pragma unroll
+            for (int t = K - 1; t > 0; --t) bq[t] = bq[t - 1];
+            bq[0] = curb;
+            const int po = z - K;
+            if (owner && po >= zc0 && po < zc1) xout[col + plane * po] = up;
+            const int tmp = wro; wro = rdo; rdo = tmp;
+            __syncthreads();
+        }
     }
 }
 
