@@ -183,4 +183,19 @@ void gpu_semilag(float *field, float *field_src, float *u, float *v, float *w, i
     BMQ_CKV(launch_semilag(kLegacy, g, full(nk + dim_z), Stag{dim_x, dim_y, dim_z}, u, v, w, 1, &field, &src, cfldt, dt));
 }
 
+// max(|u|, |v|, |w|) on the device, legacy default stream, result copied to *host_out.  Replaces the
+// serial host loops of getCFL (BimocqGPUSolver.cpp:348-373, BimocqSolver.cpp:1067-1118), which walk
+// host copies of the three face fields; the caller applies the 1e-4 floor and h / max itself.
+int bmq_max_abs3(const float *u, long long nu, const float *v, long long nv, const float *w, long long nw, float *host_out)
+{
+    if (!host_out || nu < 0 || nv < 0 || nw < 0) return set_error(BMQ_ERR_ARG, "bmq_max_abs3: bad argument");
+    if (!require_device()) return BMQ_ERR_NODEVICE;
+    static float *d_red = nullptr;   // 4-byte device scalar, allocated once per process
+    if (!d_red) BMQ_CK(cudaMalloc(&d_red, sizeof(float)));
+    BMQ_CK(cudaMemsetAsync(d_red, 0, sizeof(float), kLegacy));
+    BMQ_CK(launch_maxabs3(kLegacy, u, (size_t)nu, v, (size_t)nv, w, (size_t)nw, d_red));
+    BMQ_CK(cudaMemcpy(host_out, d_red, sizeof(float), cudaMemcpyDeviceToHost));
+    return BMQ_OK;
+}
+
 }  // extern "C"

@@ -83,9 +83,11 @@ k_forward(Grid3 g, int kbeg, int kend_, Vel3 vel, MapSetRW<NMAP> maps, float cfl
 // and the velocity, so both mappers (velocity + scalar) are updated from one evaluation.
 __device__ __forceinline__ float dmc_axis(float p, float v, float a, float s)
 {
-    // (fabs(a) > 1e-4) is a float-vs-double comparison in the reference
-    if ((double)fabsf(a) > 1e-4) return p - (1.f - expf(-a * s)) * v / a;
-    return fmaf(-v, s, p);
+    // The reference's expression, literally (GPU_kernel.cu:194-196: float-vs-double comparison, `exp`
+    // resolving to expf, int literal 1), so that nvcc/ptxas make the same contraction choices as in
+    // the reference binary.  A hand-contracted form (explicit fmaf in the Euler branch) differed by
+    // one ulp in rare cells with |v| ~ 1e-6 (found by tests/test_gpusolver_frame_gpu.py).
+    return (fabs(a) > 1e-4) ? p - (1 - exp(-a * s)) * v / a : p - v * s;
 }
 
 template <bool P2, int NMAP>

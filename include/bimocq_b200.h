@@ -128,6 +128,11 @@ void gpu_diffuse_field(float *field, float *fieldTemp0, float *filedTemp1, int n
 /* replaces GPU_Advection.h:103 (def. GPU_kernel.cu:959-964): field = coeff1*field1 + coeff2*field2 */
 void gpu_mad(float *field, float *field1, float *field2, float coeff1, float coeff2, int number);
 
+/* replaces the host loops of getCFL (BimocqGPUSolver.cpp:348-373, BimocqSolver.cpp:1067-1118):
+ * *host_out = max(|u|, |v|, |w|) over device arrays of nu, nv, nw floats (legacy default stream). */
+int bmq_max_abs3(const float *u, long long nu, const float *v, long long nv, const float *w, long long nw,
+                 float *host_out);
+
 /* ------------------------------------------------------------------ pressure projection */
 /* One multigrid level; identical layout to the reference's SCoarseLevelInfo (GPU_Advection.h:13-24),
  * so a reference-side `SCoarseLevelInfo levels[LEVEL_COUNT]` can be passed as is. */
