@@ -127,6 +127,10 @@ _PROTOS = {
     "gpu_add_buoyancy": (None, [_F] * 3 + [_I, _I, _I, _f, _f, _f]),
     "gpu_diffuse_field": (None, [_F] * 3 + [_I, _I, _I, _I, _f]),
     "gpu_mad": (None, [_F] * 3 + [_f, _f, _I]),
+    "bmq_blocked_elems": (C.c_longlong, [_I, _I, _I]),
+    "bmq_blocked_to_linear": (_I, [_F, _F, _I, _I, _I, C.c_void_p]),
+    "bmq_linear_to_blocked": (_I, [_F, _F, _I, _I, _I, C.c_void_p]),
+    "bmq3d_set_host_layout": (_I, [_H, _I]),
     "bmq_max_abs3": (_I, [_F, C.c_longlong, _F, C.c_longlong, _F, C.c_longlong, C.POINTER(_f)]),
     "gpu_multi_grid_conjugate_gradient": (None, [_F] * 3 + [_D] * 7 + [C.POINTER(CoarseLevel), _I, _I, C.c_double]),
     "bmq_mgpcg_create": (_I, [_I, _I, _I, _I, C.POINTER(_H)]),

@@ -62,6 +62,9 @@ cudaError_t launch_maxabs3(cudaStream_t s, const float *a, size_t na, const floa
                            const float *c, size_t nc, float *out_dev);
 cudaError_t launch_axpy(cudaStream_t s, float *a, const float *b, float c, size_t n);
 cudaError_t launch_add_field(cudaStream_t s, float *out, const float *a, const float *b, float c, size_t n);
+// 8^3-blocked buffer3Df layout <-> linear (sources3d.cu)
+size_t blocked_elems(int nx, int ny, int nz);
+cudaError_t launch_relayout(cudaStream_t s, bool to_linear, const float *src, float *dst, int nx, int ny, int nz);
 cudaError_t launch_identity(cudaStream_t s, const Grid3 &g, KRange r, int nsets, float *const sets[][3]);
 
 }  // namespace bmq

@@ -57,6 +57,9 @@ struct bmq3d_solver {
     bool semi_alloc = false;
     // copy streams + events of the host-buffer path (bmq3d_*_host): transfers overlap the stages
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    // host buffers in the reference's 8^3-blocked buffer3Df layout: raw transfers + relayout on the device
+    int host_layout = BMQ_LAYOUT_LINEAR;
+    float *stage_up = nullptr, *stage_down = nullptr;   // blocked staging, one per copy direction
     cudaEvent_t ev_copy[12] = {};
     // optional per-stage CUDA-event timing (bmq3d_timing_*): pairs recorded on `stream`
     bool timing = false;
@@ -504,6 +507,8 @@ int bmq3d_destroy(bmq3d_solver *s)
     for (auto e : s->ev_copy) if (e) cudaEventDestroy(e);
     for (auto &sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : s->event_pool) cudaEventDestroy(e);
+    if (s->stage_up) cudaFree(s->stage_up);
+    if (s->stage_down) cudaFree(s->stage_down);
     if (s->d_red) cudaFree(s->d_red);
     if (s->h_red) cudaFreeHost(s->h_red);
     delete s;
@@ -532,13 +537,53 @@ int bmq3d_field_ptr(bmq3d_solver *s, int field_id, float **dev_ptr, int *first_p
     return BMQ_OK;
 }
 
+// Host <-> device field transfer in the handle's host layout, enqueued on `st`.  Blocked layout
+// (gpuMapper::copyHostToDevice / copyDeviceToHost, GPU_Advection.h:249-299, minus their host-side
+// relayout loops): the raw blocked buffer crosses PCIe and a device kernel permutes it.
+static int h2d_field(bmq3d_solver *s, const Field &fd, const float *host, cudaStream_t st)
+{
+    if (s->host_layout == BMQ_LAYOUT_LINEAR) {
+        BMQ_CK(cudaMemcpyAsync(fd.alloc, host, fd.stored_elems() * sizeof(float), cudaMemcpyHostToDevice, st));
+        return BMQ_OK;
+    }
+    BMQ_CK(cudaMemcpyAsync(s->stage_up, host, blocked_elems(fd.nx, fd.ny, fd.nz) * sizeof(float), cudaMemcpyHostToDevice, st));
+    BMQ_CK(launch_relayout(st, true, s->stage_up, fd.alloc, fd.nx, fd.ny, fd.nz));
+    return BMQ_OK;
+}
+static int d2h_field(bmq3d_solver *s, const Field &fd, float *host, cudaStream_t st)
+{
+    if (s->host_layout == BMQ_LAYOUT_LINEAR) {
+        BMQ_CK(cudaMemcpyAsync(host, fd.alloc, fd.stored_elems() * sizeof(float), cudaMemcpyDeviceToHost, st));
+        return BMQ_OK;
+    }
+    BMQ_CK(launch_relayout(st, false, fd.alloc, s->stage_down, fd.nx, fd.ny, fd.nz));
+    BMQ_CK(cudaMemcpyAsync(host, s->stage_down, blocked_elems(fd.nx, fd.ny, fd.nz) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return BMQ_OK;
+}
+
+int bmq3d_set_host_layout(bmq3d_solver *s, int layout)
+{
+    NEED(s);
+    if (layout != BMQ_LAYOUT_LINEAR && layout != BMQ_LAYOUT_BLOCKED8) return set_error(BMQ_ERR_ARG, "bmq3d_set_host_layout: unknown layout %d", layout);
+    if (layout == BMQ_LAYOUT_BLOCKED8) {
+        if (s->k0 != 0 || s->k1 != s->nk) return set_error(BMQ_ERR_ARG, "bmq3d_set_host_layout: blocked host buffers need a full-domain handle");
+        if (!s->stage_up) {
+            const size_t n = blocked_elems(s->ni + 1, s->nj + 1, s->nk + 1) * sizeof(float);   // covers every field shape
+            BMQ_CK(cudaMalloc(&s->stage_up, n));
+            BMQ_CK(cudaMalloc(&s->stage_down, n));
+        }
+    }
+    s->host_layout = layout;
+    return BMQ_OK;
+}
+
 int bmq3d_upload(bmq3d_solver *s, int field_id, const float *host)
 {
     NEED(s);
     if (field_id >= BMQ_F_U_SEMI && field_id <= BMQ_F_T_SEMI) RET_IF(ensure_semi(s));
     Field *fd = field_of(s, field_id);
     if (!fd || !fd->alloc || !host) return set_error(BMQ_ERR_ARG, "bmq3d_upload: bad field id %d or null host", field_id);
-    BMQ_CK(cudaMemcpyAsync(fd->alloc, host, fd->stored_elems() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    RET_IF(h2d_field(s, *fd, host, s->stream));
     BMQ_CK(cudaStreamSynchronize(s->stream));
     return BMQ_OK;
 }
@@ -549,7 +594,7 @@ int bmq3d_download(bmq3d_solver *s, int field_id, float *host)
     if (field_id >= BMQ_F_U_SEMI && field_id <= BMQ_F_T_SEMI) RET_IF(ensure_semi(s));
     Field *fd = field_of(s, field_id);
     if (!fd || !fd->alloc || !host) return set_error(BMQ_ERR_ARG, "bmq3d_download: bad field id %d or null host", field_id);
-    BMQ_CK(cudaMemcpyAsync(host, fd->alloc, fd->stored_elems() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    RET_IF(d2h_field(s, *fd, host, s->stream));
     BMQ_CK(cudaStreamSynchronize(s->stream));
     return BMQ_OK;
 }
@@ -719,7 +764,7 @@ static int ensure_copy_streams(bmq3d_solver *s)
 
 static int upload_async(bmq3d_solver *s, Field &fd, const float *host, cudaEvent_t done)
 {
-    BMQ_CK(cudaMemcpyAsync(fd.alloc, host, fd.stored_elems() * sizeof(float), cudaMemcpyHostToDevice, s->s_h2d));
+    RET_IF(h2d_field(s, fd, host, s->s_h2d));
     BMQ_CK(cudaEventRecord(done, s->s_h2d));
     return BMQ_OK;
 }
@@ -763,7 +808,7 @@ int bmq3d_advect_host(bmq3d_solver *s, int framenum, float dt, float *u, float *
         BMQ_CK(cudaStreamWaitEvent(s->s_d2h, ev[2 + which], 0));
         for (int c = which == 0 ? 0 : 3; c < (which == 0 ? 3 : 5); ++c) {
             Field &fd = s->f[BMQ_F_U + c];
-            BMQ_CK(cudaMemcpyAsync(host[c], fd.alloc, fd.stored_elems() * sizeof(float), cudaMemcpyDeviceToHost, s->s_d2h));
+            RET_IF(d2h_field(s, fd, host[c], s->s_d2h));
         }
     }
     BMQ_CK(cudaStreamSynchronize(s->s_d2h));

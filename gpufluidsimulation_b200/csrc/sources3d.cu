@@ -9,6 +9,10 @@
 #include "common.h"
 #include "launch3d.h"
 
+namespace bmq {
+void count_launches(unsigned n);   // kernels3d.cu
+}
+
 namespace {
 
 #define SRC_IJK(fi, fj, fk)                                       \
@@ -106,9 +110,73 @@ k_mad(float *field, const float *f1, const float *f2, float c1, float c2, size_t
     for (size_t e = done + tid; e < n; e += stride) field[e] = __fmaf_rn(c1, f1[e], __fmul_rn(c2, f2[e]));
 }
 
+// ---- 8^3-blocked host container layout ------------------------------------
+// buffer3Df stores cell (i,j,k) at ((K*bx*by + J*bx + I) << 9) + (kk << 6) + (jj << 3) + ii with
+// I = i>>3, ii = i&7, ... and bx = ceil(nx/8) (include/fluid_buffer3D.h:173-189).  A warp moves 128
+// contiguous bytes of a dense row = the 32-byte rows of four neighbouring blocks: whole sectors on
+// both sides.
+template <bool TO_LINEAR>
+__global__ void __launch_bounds__(256)
+k_relayout(const float *__restrict__ src, float *__restrict__ dst, int nx, int ny, int nz, int bx, int by)
+{
+    // CTA (32, 8): lanes run along i (128 contiguous bytes of a dense row = the 32-byte rows of four
+    // blocks), threadIdx.y = jj, blockIdx.y = J, blockIdx.z = K, loop over kk.  No divisions.
+    const int i = blockIdx.x * 32 + threadIdx.x, I = i >> 3, ii = i & 7;
+    if (I >= bx) return;
+    const int J = blockIdx.y, K = blockIdx.z, jj = threadIdx.y, j = J * 8 + jj;
+    const size_t blk = ((size_t)(K * by + J) * bx + I) << 9;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const int k = K * 8 + kk;
+        const size_t e = blk + (kk << 6) + (jj << 3) + ii;
+        const bool in = i < nx && j < ny && k < nz;
+        const size_t lin = (size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k);
+        if (TO_LINEAR) {
+            if (in) dst[lin] = src[e];
+        } else {
+            dst[e] = in ? src[lin] : 0.f;   // padding cells: zero, as Buffer3D::init leaves them
+        }
+    }
+}
+
 }  // namespace
 
+namespace bmq {
+size_t blocked_elems(int nx, int ny, int nz) { return (size_t)((nx + 7) / 8) * ((ny + 7) / 8) * ((nz + 7) / 8) * 512; }
+cudaError_t launch_relayout(cudaStream_t s, bool to_linear, const float *src, float *dst, int nx, int ny, int nz)
+{
+    const int bx = (nx + 7) / 8, by = (ny + 7) / 8, bz = (nz + 7) / 8;
+    dim3 grid((bx * 8 + 31) / 32, by, bz), block(32, 8);
+    if (to_linear) k_relayout<true><<<grid, block, 0, s>>>(src, dst, nx, ny, nz, bx, by);
+    else k_relayout<false><<<grid, block, 0, s>>>(src, dst, nx, ny, nz, bx, by);
+    count_launches(1);
+    return cudaGetLastError();
+}
+}  // namespace bmq
+
 extern "C" {
+
+long long bmq_blocked_elems(int nx, int ny, int nz)
+{
+    if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+    return (long long)bmq::blocked_elems(nx, ny, nz);
+}
+
+int bmq_blocked_to_linear(const float *blocked_dev, float *linear_dev, int nx, int ny, int nz, void *stream)
+{
+    if (!blocked_dev || !linear_dev || nx <= 0 || ny <= 0 || nz <= 0) return bmq::set_error(BMQ_ERR_ARG, "bmq_blocked_to_linear: bad argument");
+    if (!bmq::require_device()) return BMQ_ERR_NODEVICE;
+    BMQ_CK(bmq::launch_relayout((cudaStream_t)stream, true, blocked_dev, linear_dev, nx, ny, nz));
+    return BMQ_OK;
+}
+
+int bmq_linear_to_blocked(const float *linear_dev, float *blocked_dev, int nx, int ny, int nz, void *stream)
+{
+    if (!blocked_dev || !linear_dev || nx <= 0 || ny <= 0 || nz <= 0) return bmq::set_error(BMQ_ERR_ARG, "bmq_linear_to_blocked: bad argument");
+    if (!bmq::require_device()) return BMQ_ERR_NODEVICE;
+    BMQ_CK(bmq::launch_relayout((cudaStream_t)stream, false, linear_dev, blocked_dev, nx, ny, nz));
+    return BMQ_OK;
+}
 
 void gpu_emit_smoke(float *u, float *v, float *w, float *rho, float *T, float h, int ni, int nj, int nk, float centerX,
                     float centerY, float centerZ, float radius, float density, float temperature, float emiter)

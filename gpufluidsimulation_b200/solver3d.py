@@ -269,15 +269,25 @@ class BimocqAdvection3D:
         ptr, p0, npl, nx, ny = self.field_info(name)
         return torch.as_tensor(_DevView(ptr, (npl, ny, nx)), device="cuda")
 
+    def set_host_layout(self, blocked: bool):
+        """Host buffers of upload / download / *_host are dense x-fastest (default) or the reference's
+        8^3-blocked buffer3Df storage (include/fluid_buffer3D.h:173-189), relaid out on the device."""
+        check(self.lib.bmq3d_set_host_layout(self._h, 1 if blocked else 0), "bmq3d_set_host_layout")
+        self._blocked = bool(blocked)
+
+    def host_elems(self, name):
+        _, _, npl, nx, ny = self.field_info(name)
+        return int(self.lib.bmq_blocked_elems(nx, ny, npl)) if getattr(self, "_blocked", False) else npl * nx * ny
+
     def upload(self, name, host):
         host = np.ascontiguousarray(host, dtype=np.float32)
-        _, _, npl, nx, ny = self.field_info(name)
-        assert host.size == npl * nx * ny, (name, host.shape, (npl, ny, nx))
+        assert host.size == self.host_elems(name), (name, host.shape, self.host_elems(name))
         check(self.lib.bmq3d_upload(self._h, FIELD[name], host.ctypes.data_as(C.c_void_p)), "bmq3d_upload")
 
     def download(self, name):
         _, _, npl, nx, ny = self.field_info(name)
-        out = np.empty((npl, ny, nx), dtype=np.float32)
+        out = (np.empty(self.host_elems(name), dtype=np.float32) if getattr(self, "_blocked", False)
+               else np.empty((npl, ny, nx), dtype=np.float32))
         check(self.lib.bmq3d_download(self._h, FIELD[name], out.ctypes.data_as(C.c_void_p)), "bmq3d_download")
         return out
 

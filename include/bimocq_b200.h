@@ -133,6 +133,17 @@ void gpu_mad(float *field, float *field1, float *field2, float coeff1, float coe
 int bmq_max_abs3(const float *u, long long nu, const float *v, long long nv, const float *w, long long nw,
                  float *host_out);
 
+/* ------------------------------------------------------------------ blocked host containers */
+/* The reference's host fields are buffer3Df: 8x8x8 blocks, cell (i,j,k) at
+ * ((K*bx*by + J*bx + I) << 9) + (kk << 6) + (jj << 3) + ii, bx = ceil(nx/8), padded to whole blocks
+ * (include/fluid_buffer3D.h:56-75,173-189).  gpuMapper::copyHostToDevice / copyDeviceToHost
+ * (GPU_Advection.h:249-299) relayout them on the HOST before / after every transfer; these do it on
+ * the device.  bmq_blocked_elems = the physical element count Buffer3D allocates. */
+long long bmq_blocked_elems(int nx, int ny, int nz);
+int bmq_blocked_to_linear(const float *blocked_dev, float *linear_dev, int nx, int ny, int nz, void *cuda_stream);
+/* padding cells of the blocked buffer are written as 0 (what Buffer3D::init leaves there) */
+int bmq_linear_to_blocked(const float *linear_dev, float *blocked_dev, int nx, int ny, int nz, void *cuda_stream);
+
 /* ------------------------------------------------------------------ pressure projection */
 /* One multigrid level; identical layout to the reference's SCoarseLevelInfo (GPU_Advection.h:13-24),
  * so a reference-side `SCoarseLevelInfo levels[LEVEL_COUNT]` can be passed as is. */
@@ -170,6 +181,14 @@ int  bmq_mgpcg_levels(bmq_mgpcg *m, bmq_coarse_level *out, int capacity);
 
 /* ------------------------------------------------------------------ handle API (3D) */
 typedef struct bmq3d_solver bmq3d_solver;
+
+/* Layout of the HOST buffers passed to bmq3d_upload / bmq3d_download / bmq3d_advect_host /
+ * bmq3d_accumulate_host: dense x-fastest (default), or the reference's 8^3-blocked buffer3Df
+ * (`buffer3Df::_data->getPtr()`, bmq_blocked_elems floats per field) -- then the raw blocked buffer
+ * is transferred and relaid out on the device, replacing gpuMapper::copyHostToDevice /
+ * copyDeviceToHost (GPU_Advection.h:249-299).  Full-domain handles only. */
+enum { BMQ_LAYOUT_LINEAR = 0, BMQ_LAYOUT_BLOCKED8 = 1 };
+int bmq3d_set_host_layout(bmq3d_solver *s, int layout);
 
 /* Field identifiers for bmq3d_field_ptr / bmq3d_upload / bmq3d_download.  Velocity faces are
  * (ni+1)*nj*nk, ni*(nj+1)*nk, ni*nj*(nk+1); everything else ni*nj*nk.  Dense, x-fastest. */

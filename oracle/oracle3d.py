@@ -243,6 +243,30 @@ def gpu_multi_grid_conjugate_gradient(u, v, w, levels=6, iters=50, halfrdx=0.5, 
     return out
 
 
+def blocked_index(nx, ny, nz):
+    """Storage index of cell (i,j,k) in the reference's 8^3-blocked Buffer3D (include/fluid_buffer3D.h:173-189),
+    as an int64 array of shape (nz, ny, nx), and the physical element count (:56-75)."""
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    bx, by, bz = (nx + 7) // 8, (ny + 7) // 8, (nz + 7) // 8
+    idx = ((((k >> 3) * bx * by + (j >> 3) * bx + (i >> 3)) << 9) + ((k & 7) << 6) + ((j & 7) << 3) + (i & 7)).astype(np.int64)
+    return idx, bx * by * bz * 512
+
+
+def linear_to_blocked(linear):
+    """Buffer3D storage (padding = 0) holding the dense (nz, ny, nx) array `linear`."""
+    nz, ny, nx = linear.shape
+    idx, n = blocked_index(nx, ny, nz)
+    out = np.zeros(n, dtype=linear.dtype)
+    out[idx.ravel()] = linear.ravel()
+    return out
+
+
+def blocked_to_linear(blocked, nx, ny, nz):
+    idx, n = blocked_index(nx, ny, nz)
+    assert blocked.size == n
+    return blocked[idx.ravel()].reshape(nz, ny, nx)
+
+
 def identity_maps(ni, nj, nk, h):
     """Mapping.cpp:310-324: x = (float)i * h etc."""
     h32 = np.float32(h)

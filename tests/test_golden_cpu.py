@@ -117,3 +117,15 @@ def test_projection_oracle_matches_reference_golden(oracle):
         assert np.array_equal(a, g[name]), name
     assert np.array_equal(out["result"][: 2 * iters + 3], g["result"][: 2 * iters + 3])
     assert np.array_equal(out["result"][2000:2001 + iters], g["result"][2000:2001 + iters])
+
+
+def test_blocked_layout_restatement_matches_reference_container(oracle):
+    """numpy restatement of Buffer3D's block indexing against storage written by the reference's own
+    class (tests/golden/ref_blocked_layout.npz, made on CPU by tests/golden/make_golden_blocked.py)."""
+    g = np.load(os.path.join(HERE, "golden", "ref_blocked_layout.npz"))
+    for nx, ny, nz in g["shapes"]:
+        nx, ny, nz = int(nx), int(ny), int(nz)
+        lin = (np.arange(nx * ny * nz, dtype=np.float32) + 1).reshape(nz, ny, nx)
+        want = g[f"blocked_{nx}x{ny}x{nz}"]
+        assert np.array_equal(oracle.linear_to_blocked(lin), want)
+        assert np.array_equal(oracle.blocked_to_linear(want, nx, ny, nz), lin)

@@ -113,6 +113,15 @@ def source_terms(n=512):
     out["gpu_diffuse_field(20 sweeps)"] = {"ms": t, "alg_GBps": (20 * 3 + 4) * 4 * cells / t / 1e6}   # per sweep R field,in + W out
     t = timed(lambda: lib.gpu_mad(p(c), p(a), p(b), 0.5, 0.25, cells))
     out["gpu_mad"] = {"ms": t, "alg_GBps": 3 * 4 * cells / t / 1e6}
+    # 8^3-blocked host container layout <-> dense: one read + one write per element
+    nb = int(lib.bmq_blocked_elems(n + 1, n, n))
+    import torch
+    blk = torch.zeros(nb, dtype=torch.float32, device="cuda")
+    u = alloc_field((n, n, n + 1)); u.normal_()
+    t = timed(lambda: lib.bmq_linear_to_blocked(p(u), p(blk), n + 1, n, n, None))
+    out["bmq_linear_to_blocked(u faces)"] = {"ms": t, "alg_GBps": 4 * (u.numel() + nb) / t / 1e6}
+    t = timed(lambda: lib.bmq_blocked_to_linear(p(blk), p(u), n + 1, n, n, None))
+    out["bmq_blocked_to_linear(u faces)"] = {"ms": t, "alg_GBps": 4 * (u.numel() + nb) / t / 1e6}
     print(json.dumps({"source_terms_512": out}, indent=1))
 
 
