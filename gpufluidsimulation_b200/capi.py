@@ -127,6 +127,7 @@ _PROTOS = {
     "gpu_add_buoyancy": (None, [_F] * 3 + [_I, _I, _I, _f, _f, _f]),
     "gpu_diffuse_field": (None, [_F] * 3 + [_I, _I, _I, _I, _f]),
     "gpu_mad": (None, [_F] * 3 + [_f, _f, _I]),
+    "gpu_clamp_extrema": (None, [_F] * 5 + [_I] * 6 + [_f] * 5),
     "bmq_blocked_elems": (C.c_longlong, [_I, _I, _I]),
     "bmq_blocked_to_linear": (_I, [_F, _F, _I, _I, _I, C.c_void_p]),
     "bmq_linear_to_blocked": (_I, [_F, _F, _I, _I, _I, C.c_void_p]),

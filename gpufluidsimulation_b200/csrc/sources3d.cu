@@ -110,6 +110,50 @@ k_mad(float *field, const float *f1, const float *f2, float c1, float c2, size_t
     for (size_t e = done + tid; e < n; e += stride) field[e] = __fmaf_rn(c1, f1[e], __fmul_rn(c2, f2[e]));
 }
 
+// clamp_extrema_kernel, GPU_kernel.cu:892-941 (MacCormack / Reflection schemes,
+// BimocqGPUSolver.cpp:232-338): every field cell is traced back with a midpoint step and the value
+// of fieldTemp AT THE BACK-TRACED CELL is replaced by the trilinear sample of `field` when it lies
+// outside the range of the eight surrounding values.  Reproduced literally, including
+//   * the grid index taken as floor(position) without dividing by h (:913-915), so for the shipped
+//     scenes (L = 0.2) every thread addresses cell (0,0,0) or (-1,..);
+//   * the scatter: several threads may write the same fieldTemp cell (a race in the reference; the
+//     result there is the value of whichever thread wins -- same here).
+// Only difference: reads past the end of `field` return 0 and writes outside fieldTemp are dropped
+// (the reference accesses whatever memory is there).
+__global__ void __launch_bounds__(128)
+k_clamp_extrema_mc(const float *__restrict__ field, float *fieldTemp, bmq::Vel3 vel, int ni, int nj, int nk, int dimx,
+                   int dimy, int dimz, float ox, float oy, float oz, float h, float dt)
+{
+    SRC_IJK(ni, nj, nk)
+    (void)index;
+    bmq::Grid3 g;
+    g.ni = ni - dimx; g.nj = nj - dimy; g.nk = nk - dimz; g.h = h; g.inv_h = 1.0f / h;
+    const float ptx = h * (float(i) + ox), pty = h * (float(j) + oy), ptz = h * (float(k) + oz);
+    float3 v = bmq::get_velocity_ref(vel, g, ptx, pty, ptz);
+    const float halfdt = 0.5f * dt;
+    float pxx = ptx - v.x * halfdt, pxy = pty - v.y * halfdt, pxz = ptz - v.z * halfdt;
+    v = bmq::get_velocity_ref(vel, g, pxx, pxy, pxz);
+    pxx = ptx - v.x * dt; pxy = pty - v.y * dt; pxz = ptz - v.z * dt;
+    const int gi = (int)floor(pxx), gj = (int)floor(pxy), gk = (int)floor(pxz);
+    const float cx = pxx - (float)gi, cy = pxy - (float)gj, cz = pxz - (float)gk;
+    const long long ol = (long long)gk * nj * ni + (long long)gj * ni + gi;
+    const long long total = (long long)ni * nj * nk;
+    if (ol < 0 || ol >= total) return;                      // the reference would write outside the array
+    auto at = [&](long long q) -> float { return q < total ? field[q] : 0.f; };   // reads past the end: zero padding
+    const long long sy = ni, sz = (long long)nj * ni;
+    const int o = (int)ol;
+    const float v0 = at(ol), v1 = at(ol + 1), v2 = at(ol + sy), v3 = at(ol + sy + 1);
+    const float v4 = at(ol + sz), v5 = at(ol + sz + 1), v6 = at(ol + sz + sy), v7 = at(ol + sz + sy + 1);
+    const float mn = min(v0, min(v1, min(v2, min(v3, min(v4, min(v5, min(v6, v7)))))));
+    const float mx = max(v0, max(v1, max(v2, max(v3, max(v4, max(v5, max(v6, v7)))))));
+    const float temp = fieldTemp[o];
+    if (temp < mn || temp > mx) {
+        const float iv1 = bmq::lerp_ref(bmq::lerp_ref(v0, v1, cx), bmq::lerp_ref(v2, v3, cx), cy);
+        const float iv2 = bmq::lerp_ref(bmq::lerp_ref(v4, v5, cx), bmq::lerp_ref(v6, v7, cx), cy);
+        fieldTemp[o] = bmq::lerp_ref(iv1, iv2, cz);
+    }
+}
+
 // ---- 8^3-blocked host container layout ------------------------------------
 // buffer3Df stores cell (i,j,k) at ((K*bx*by + J*bx + I) << 9) + (kk << 6) + (jj << 3) + ii with
 // I = i>>3, ii = i&7, ... and bx = ceil(nx/8) (include/fluid_buffer3D.h:173-189).  A warp moves 128
@@ -176,6 +220,16 @@ int bmq_linear_to_blocked(const float *linear_dev, float *blocked_dev, int nx, i
     if (!bmq::require_device()) return BMQ_ERR_NODEVICE;
     BMQ_CK(bmq::launch_relayout((cudaStream_t)stream, false, linear_dev, blocked_dev, nx, ny, nz));
     return BMQ_OK;
+}
+
+void gpu_clamp_extrema(float *field, float *fieldTemp, float *u, float *v, float *w, int ni, int nj, int nk, int dimx, int dimy,
+                       int dimz, float ox, float oy, float oz, float h, float dt)
+{
+    if (!bmq::require_device()) return;
+    bmq::Vel3 vel{u, v, w};
+    k_clamp_extrema_mc<<<sgrd(ni, nj, nk), sblk()>>>(field, fieldTemp, vel, ni, nj, nk, dimx, dimy, dimz, ox, oy, oz, h, dt);
+    bmq::count_launches(1);
+    BMQ_CKV(cudaGetLastError());
 }
 
 void gpu_emit_smoke(float *u, float *v, float *w, float *rho, float *T, float h, int ni, int nj, int nk, float centerX,

@@ -133,6 +133,13 @@ void gpu_mad(float *field, float *field1, float *field2, float coeff1, float coe
 int bmq_max_abs3(const float *u, long long nu, const float *v, long long nv, const float *w, long long nw,
                  float *host_out);
 
+/* replaces GPU_Advection.h:101 (def. GPU_kernel.cu:892-950; MacCormack / Reflection schemes,
+ * BimocqGPUSolver.cpp:232-338).  ni,nj,nk are the FIELD's dimensions, dim* its staggering, o* the
+ * sample offset in cells.  Literal reproduction, units slip (:913-915) and scatter included; reads
+ * past the end of `field` return 0, writes outside `fieldTemp` are dropped. */
+void gpu_clamp_extrema(float *field, float *fieldTemp, float *u, float *v, float *w, int ni, int nj, int nk,
+                       int dimx, int dimy, int dimz, float ox, float oy, float oz, float h, float dt);
+
 /* ------------------------------------------------------------------ blocked host containers */
 /* The reference's host fields are buffer3Df: 8x8x8 blocks, cell (i,j,k) at
  * ((K*bx*by + J*bx + I) << 9) + (kk << 6) + (jj << 3) + ii, bx = ceil(nx/8), padded to whole blocks

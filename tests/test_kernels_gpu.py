@@ -251,3 +251,46 @@ def test_mad(case, oracle, ours, ref):
     a, b = c.fields["u"], c.fields2["u"]
     args = [np.zeros_like(a), a, b, 0.75, -1.25, a.size]
     _three_way("gpu_mad", args, lambda x: oracle.gpu_mad(x[0], x[1], x[2], 0.75, -1.25), ours, ref, [0])
+
+
+@pytest.mark.parametrize("stag", [(0, 0, 0, 0.0, 0.0, 0.0), (1, 0, 0, 0.5, 0.0, 0.0), (0, 0, 1, 0.0, 0.0, 0.5)], ids=["centred", "u", "w"])
+def test_clamp_extrema_macCormack_matches_reference(stag):
+    """gpu_clamp_extrema (GPU_kernel.cu:892-950) scatters to the back-traced cell, so two threads may
+    hit one cell (a race in the reference).  With a uniform velocity every thread lands on its own
+    cell and the kernel is deterministic; h = 1 makes the reference's floor(position) a cell index."""
+    ref = load_reference_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref3d.so not built")
+    from gpufluidsimulation_b200 import capi
+
+    ours = capi.load_library()
+    ni, nj, nk = 24, 20, 28
+    dx, dy, dz, ox, oy, oz = stag
+    rng = np.random.default_rng(17)
+    field = rng.standard_normal((nk + dz, nj + dy, ni + dx)).astype(np.float32)
+    temp = (field + 0.8 * rng.standard_normal(field.shape)).astype(np.float32)
+    u = np.full((nk, nj, ni + 1), 0.5, np.float32)
+    v = np.full((nk, nj + 1, ni), -0.25, np.float32)
+    w = np.full((nk + 1, nj, ni), 1.75, np.float32)
+    import torch
+
+    def run(lib):
+        # the kernel samples the velocity up to two cells outside the grid (no bounds checks in the
+        # reference): every array sits in the middle of a zeroed allocation three times its size
+        dev = []
+        for a in (field, temp, u, v, w):
+            big = torch.zeros(3 * a.size, dtype=torch.float32, device="cuda")
+            t = big[a.size:2 * a.size].view(*a.shape)
+            t.copy_(torch.from_numpy(a))
+            dev.append((big, t))
+        F = C.POINTER(C.c_float)
+        fn = lib.gpu_clamp_extrema
+        fn.restype, fn.argtypes = capi._PROTOS["gpu_clamp_extrema"]
+        torch.cuda.synchronize()
+        fn(*[C.cast(C.c_void_p(t.data_ptr()), F) for _, t in dev], ni + dx, nj + dy, nk + dz, dx, dy, dz, ox, oy, oz, 1.0, 1.0)
+        torch.cuda.synchronize()
+        return dev[1][1].cpu().numpy()
+
+    got, want = run(ours), run(ref)
+    assert np.array_equal(got, want)
+    assert (got != temp).sum() > 100          # the kernel did replace values
