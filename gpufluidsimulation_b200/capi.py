@@ -134,6 +134,8 @@ _PROTOS = {
     "bmq3d_set_host_layout": (_I, [_H, _I]),
     "bmq_max_abs3": (_I, [_F, C.c_longlong, _F, C.c_longlong, _F, C.c_longlong, C.POINTER(_f)]),
     "gpu_multi_grid_conjugate_gradient": (None, [_F] * 3 + [_D] * 7 + [C.POINTER(CoarseLevel), _I, _I, C.c_double]),
+    "gpu_conjugate_gradient": (None, [_F] * 8 + [_I, _I, _I, _I, _f]),
+    "gpu_projection_jacobi": (None, [_F] * 7 + [_I, _I, _I, _I, _f, _f, _f]),
     "bmq_mgpcg_create": (_I, [_I, _I, _I, _I, C.POINTER(_H)]),
     "bmq_mgpcg_destroy": (None, [_H]),
     "bmq_mgpcg_set_stream": (_I, [_H, C.c_void_p]),

@@ -5,14 +5,15 @@
  * Two groups of entry points:
  *
  *  1. LEGACY DROP-IN SYMBOLS.  The 14 hot-path `extern "C" void gpu_*` functions of the
- *     reference, with byte-identical prototypes, so that the reference's gpuMapper /
+ *     reference -- and, widened per SURVEY 8(f), the other 8 (source terms, clamp, the three
+ *     pressure solvers): all 22 of GPU_Advection.h:26-108 -- with byte-identical prototypes, so that the reference's gpuMapper /
  *     MapperBase / MapperBaseGPU (bimocq3D/GPU_Advection.h:110-627, bimocq3D/Mapping.cpp) link
  *     against this library unchanged.  Each prototype cites the reference declaration it
  *     replaces.  All pointers are DEVICE pointers to dense x-fastest float arrays
  *     (idx = i + nx*j + nx*ny*k) of the sizes the reference uses; they run on the legacy
  *     default stream, return void, and latch errors for bmq_last_error().
  *
- *  2. HANDLE API (bmq3d_*).  Device-resident solver state with the fused kernels and the
+ *  2. HANDLE API (bmq3d_*, bmq2d_*, bmq_mgpcg_*).  Device-resident solver state with the fused kernels and the
  *     reinitialisation scheduler of BimocqSolver::advanceBimocq (bimocq3D/BimocqSolver.cpp:88-230)
  *     inside.  Returns int status codes (0 = BMQ_OK), never exits the process.
  *
@@ -171,6 +172,18 @@ typedef struct bmq_coarse_level {
 void gpu_multi_grid_conjugate_gradient(float *u, float *v, float *w, double *div, double *p, double *dir,
                                        double *residual, double *temp0, double *temp1, double *tempResult,
                                        bmq_coarse_level *levels, int levelNum, int iter, double halfrdx);
+
+/* replaces GPU_Advection.h:105 (def. GPU_kernel.cu:1345-1419): fp32 CG on lap p = halfrdx*div(u,v,w)
+ * starting from the caller's p, `iter` iterations, then u,v,w -= halfrdx*grad p.  dotResult: >= 4096
+ * floats (CG scalars at [0..2*iter+2], max residual at [2000..2000+iter]).  The reference compiles
+ * its call site out (BimocqGPUSolver.cpp:423-441) but exports the symbol. */
+void gpu_conjugate_gradient(float *u, float *v, float *w, float *div, float *p, float *residual, float *dir,
+                            float *dotResult, int ni, int nj, int nk, int iter, float halfrdx);
+/* replaces GPU_Advection.h:99 (def. GPU_kernel.cu:1816-1886): `iter` fp32 Jacobi sweeps
+ * p <- (sum of six neighbours + alpha*div)*beta between p and p_temp; like the reference, the
+ * gradient is taken of the iterate BEFORE the last one (:1866-1884).  debugParam: >= 4096 floats. */
+void gpu_projection_jacobi(float *u, float *v, float *w, float *div, float *p, float *p_temp, float *debugParam,
+                           int ni, int nj, int nk, int iter, float halfrdx, float alpha, float beta);
 
 /* Handle that owns the fp64 work buffers BimocqGPUSolver's constructor allocates
  * (BimocqGPUSolver.cpp:56-90): div, p, dir, residual, temp0, temp1, tempResult[4096] and `levels`

@@ -175,3 +175,72 @@ def test_fullsize_property_pressure_equation():
     rmax = pp.buffer("residual").abs().max().item()   # (the history holds max(r), not max|r|: calc_max has no abs)
     assert defect <= 0.5 * rmax + 1e-5, (defect, rmax)
     pp.close()
+
+
+# ---- the two fp32 solvers the reference exports but does not call (GPU_kernel.cu:1345-1419, 1816-1886)
+def _run_f32(lib, name, ni, nj, nk, iters):
+    import ctypes as C
+
+    import torch
+
+    from gpufluidsimulation_b200 import capi
+    from gpufluidsimulation_b200.solver3d import alloc_field
+
+    fn = getattr(lib, name)
+    fn.restype, fn.argtypes = capi._PROTOS[name]
+    F = C.POINTER(C.c_float)
+    n = ni * nj * nk
+    vel = []
+    for a in velocity(ni, nj, nk):
+        t = alloc_field(a.shape)
+        t.copy_(torch.from_numpy(a))
+        vel.append(t)
+    bufs = [alloc_field((nk, nj, ni)) for _ in range(4)]      # div, p, (residual | p_temp), dir
+    res = torch.zeros(4096 + 64, dtype=torch.float32, device="cuda")[:4096]
+    d = lambda t: C.cast(C.c_void_p(t.data_ptr()), F)
+    torch.cuda.synchronize()
+    if name == "gpu_conjugate_gradient":
+        fn(*[d(t) for t in vel], d(bufs[0]), d(bufs[1]), d(bufs[2]), d(bufs[3]), d(res), ni, nj, nk, iters, 0.5)
+    else:
+        fn(*[d(t) for t in vel], d(bufs[0]), d(bufs[1]), d(bufs[2]), d(res), ni, nj, nk, iters, 0.5, -1.0, 1.0 / 6.0)
+    torch.cuda.synchronize()
+    out = {k: t.cpu().numpy() for k, t in zip(("u", "v", "w", "div", "p", "aux"), vel + bufs[:3])}
+    out["result"] = res.cpu().numpy()
+    return out
+
+
+@pytest.mark.parametrize("case", [(24, 20, 28, 6), (40, 36, 44, 5)], ids=["24x20x28", "40x36x44"])
+def test_fp32_conjugate_gradient_vs_reference_kernels(case):
+    ref = load_reference_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref3d.so not built")
+    from gpufluidsimulation_b200 import capi
+
+    ni, nj, nk, iters = case
+    ours = _run_f32(capi.load_library(), "gpu_conjugate_gradient", ni, nj, nk, iters)
+    capi.check_legacy("gpu_conjugate_gradient")
+    theirs = _run_f32(ref, "gpu_conjugate_gradient", ni, nj, nk, iters)
+    for k in ("u", "v", "w", "div", "p", "aux"):
+        assert np.array_equal(ours[k], theirs[k]), k
+    assert np.array_equal(ours["result"][: 2 * iters + 3], theirs["result"][: 2 * iters + 3])
+    assert np.array_equal(ours["result"][2000:2001 + iters], theirs["result"][2000:2001 + iters])
+    assert np.isfinite(ours["p"]).all() and np.abs(ours["p"]).max() > 0
+
+
+@pytest.mark.parametrize("iters", [7, 8], ids=["odd", "even"])
+def test_fp32_jacobi_projection_vs_reference_kernels(iters):
+    """Odd / even sweep counts end in different buffers (GPU_kernel.cu:1866-1869).  The diagnostics in
+    debugParam depend on uninitialised scratch in the reference (its cudaMalloc'd residual ring) and are
+    not compared."""
+    ref = load_reference_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref3d.so not built")
+    from gpufluidsimulation_b200 import capi
+
+    ni, nj, nk = 40, 36, 44
+    ours = _run_f32(capi.load_library(), "gpu_projection_jacobi", ni, nj, nk, iters)
+    capi.check_legacy("gpu_projection_jacobi")
+    theirs = _run_f32(ref, "gpu_projection_jacobi", ni, nj, nk, iters)
+    for k in ("u", "v", "w", "div", "p", "aux"):
+        assert np.array_equal(ours[k], theirs[k]), k
+    assert np.abs(ours["p"]).max() > 0
