@@ -296,13 +296,17 @@ def run_gpu(args):
         }
 
     # ---- e2e: the same metric through the C-ABI host-buffer calls (pinned host memory, copies timed)
-    if world == 1 and not args.no_e2e:
+    if world > 1 and not args.no_e2e:
+        e2e = measure_e2e_slabs(solver, torch, dist, n, args, frame, world)
+        if rank == 0:
+            line["e2e"] = e2e
+    elif world == 1 and not args.no_e2e:
         e2e = measure_e2e(solver, torch, n, args, frame)
         if line is not None:
             line["e2e"] = e2e
     elif line is not None:
         line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                       "note": "e2e through host buffers is measured at N=1"}
+                       "note": "skipped (--no-e2e)"}
 
     if world == 1 and rank == 0 and not args.no_2d:
         try:
@@ -398,6 +402,36 @@ def measure_e2e(solver, torch, n, args, frame):
     return {"value": n ** 3 * steps / total, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": total / steps * 1e3, "steps": steps,
             "path": "bmq3d_advect_host + bmq3d_accumulate_host (C ABI), pinned host buffers"}
+
+
+def measure_e2e_slabs(solver, torch, dist, n, args, frame, world):
+    """The same step through host buffers on N GPUs: every rank uploads / downloads the planes it owns
+    over its own PCIe link (ZSlabAdvection3D.advect_host / accumulate_host), halos travel over NVLink
+    as in the device-resident step.  Time = max over ranks between two barriers."""
+    host = solver.alloc_host()
+    for hb, nm in zip(host, ("U", "V", "W", "RHO", "T")):
+        hb.copy_(solver.owned(nm))
+    torch.cuda.synchronize()
+    nbytes = [hb.numel() * 4 for hb in host]
+    counts = torch.tensor([float(sum(nbytes[:3]) * 2 + sum(nbytes)), float(sum(nbytes))], device="cuda")
+    dist.all_reduce(counts)
+    steps = max(2, min(args.steps, 4))
+    total = 0.0
+    for it in range(1 + steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        solver.advect_host(frame, DT, host)
+        solver.accumulate_host(frame, DT, host[:3], host)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        frame += 1
+        if it > 0:
+            total += float(t.item())
+    return {"value": n ** 3 * steps / total, "unit": UNIT, "h2d_bytes_per_step": int(counts[0].item()),
+            "d2h_bytes_per_step": int(counts[1].item()), "ms_per_step": total / steps * 1e3, "steps": steps,
+            "path": f"ZSlabAdvection3D.advect_host + accumulate_host on {world} ranks, pinned host buffers of the owned planes"}
 
 
 _REAL_STDOUT = None

@@ -517,6 +517,52 @@ class ZSlabAdvection3D:
     def accumulate(self, frame, dt):
         self.stepper.accumulate(frame, dt)
 
+    # ---- host-buffer step (what bmq3d_advect_host / bmq3d_accumulate_host are on one GPU): every rank
+    # moves only the planes it owns across its own PCIe link
+    def owned(self, name):
+        """torch view of the planes of `name` this rank owns (w-type fields: the top face belongs to
+        the last rank)."""
+        _, p0, _, _, _ = self.r.solver.field_info(name)
+        kb, ke = self.r.k0, self.r.k1 + (1 if name in W_TYPE and self.r.k1 == self.r.nk else 0)
+        return self.r.solver.field(name)[kb - p0:ke - p0]
+
+    def alloc_host(self):
+        """Pinned host buffers for the owned planes of u, v, w, rho, T."""
+        return [self.torch.empty(tuple(self.owned(n).shape), dtype=self.torch.float32).pin_memory() for n in CUR]
+
+    def advect_host(self, frame, dt, host):
+        """host: five pinned tensors (owned planes); u, v, w are uploaded, all five come back advected."""
+        for n, hb in zip(CUR[:3], host[:3]):
+            self.owned(n).copy_(hb, non_blocking=True)
+        self.stepper.advect(frame, dt)
+        for n, hb in zip(CUR, host):
+            hb.copy_(self.owned(n), non_blocking=True)
+        self.torch.cuda.synchronize()
+
+    def accumulate_host(self, frame, dt, forced, final):
+        """forced: u, v, w after the external forces; final: u, v, w, rho, T after projection (owned
+        planes, pinned).  The change fields are formed on the device as the reference forms them on the
+        host (BimocqSolver.cpp:149-162): d_ext = forced - advected, d_proj = final - forced,
+        d_scalar = final - advected; the current fields become `final`."""
+        from .solver3d import _dp
+        lib, torch = self.lib, self.torch
+        if getattr(self, "_stage", None) is None:
+            self._stage = torch.empty(max(self.owned(n).numel() for n in CUR), dtype=torch.float32, device=self.owned("U").device)
+        for c, n in enumerate(CUR):
+            cur, ext = self.owned(n), self.owned(CHANGE[c])
+            stage = self._stage[:cur.numel()].view(cur.shape)
+            stage.copy_(final[c], non_blocking=True)
+            if c < 3:
+                proj = self.owned(CHANGE[5 + c])
+                proj.copy_(forced[c], non_blocking=True)
+                lib.gpu_add_field(_dp(ext), _dp(proj), _dp(cur), -1.0, cur.numel())      # forced - advected
+                lib.gpu_add_field(_dp(proj), _dp(stage), _dp(proj), -1.0, cur.numel())   # final - forced
+            else:
+                lib.gpu_add_field(_dp(ext), _dp(stage), _dp(cur), -1.0, cur.numel())     # final - advected
+            cur.copy_(stage)
+        self.stepper.accumulate(frame, dt)
+        torch.cuda.synchronize()
+
     def apply_buoyancy(self, beta, dt, alpha=0.0):
         # local operation on the stored planes (owned planes are what matters; halos are refreshed
         # by the exchange that precedes every consumer)

@@ -47,8 +47,32 @@ def run(transport, rank, world, ni, nj, nk, h, halo, frames, dt, u, v, w, rho, T
                 err = (got[kb - p0:ke - p0] - want[kb:ke]).abs().max().item()
                 print(f"[{transport}] rank {rank} frame {frame} field {name}: MISMATCH max abs {err}", flush=True)
                 sys.exit(1)
+    # host-buffer step: owned planes through pinned host memory on every rank vs the single-GPU C path
+    host = z.alloc_host()
+    full = [torch.empty(tuple(single.field(n).shape), dtype=torch.float32).pin_memory() for n in zslab.CUR]
+    for hb, fb, n in zip(host, full, zslab.CUR):
+        hb.copy_(z.owned(n)); fb.copy_(single.field(n))
+    torch.cuda.synchronize()
+    for frame in range(frames, frames + 2):
+        z.advect_host(frame, dt, host)
+        single.advect_host(frame, dt, *full)
+        forced_z = [h.clone().pin_memory() for h in host[:3]]; forced_s = [f.clone().pin_memory() for f in full[:3]]
+        forced_z[1] *= 1.01; forced_s[1] *= 1.01
+        final_z = [0.98 * f for f in forced_z] + host[3:]; final_s = [0.98 * f for f in forced_s] + full[3:]
+        z.accumulate_host(frame, dt, forced_z, final_z)
+        single.accumulate_host(frame, dt, forced_s, final_s)
+        for hb, fz in zip(host[:3], final_z[:3]):
+            hb.copy_(fz)
+        for fb, fs in zip(full[:3], final_s[:3]):
+            fb.copy_(fs)
+        for name in zslab.CUR + zslab.INIT + zslab.CHANGE:
+            _, p0, _, _, _ = single.field_info(name)
+            kb, ke = z.r.k0, z.r.k1 + (1 if name in zslab.W_TYPE and z.r.k1 == nk else 0)
+            if not torch.equal(z.owned(name), single.field(name)[kb:ke]):
+                print(f"[{transport}] host path, rank {rank} frame {frame} field {name}: MISMATCH", flush=True)
+                sys.exit(1)
     if rank == 0:
-        print(f"[{transport}] bit-identical to the single-GPU run over {frames} frames", z.stats(), flush=True)
+        print(f"[{transport}] bit-identical to the single-GPU run over {frames} frames (+2 through host buffers)", z.stats(), flush=True)
     z.close(); single.close()
 
 
