@@ -60,7 +60,7 @@ struct bmq3d_solver {
     // host buffers in the reference's 8^3-blocked buffer3Df layout: raw transfers + relayout on the device
     int host_layout = BMQ_LAYOUT_LINEAR;
     float *stage_up = nullptr, *stage_down = nullptr;   // blocked staging, one per copy direction
-    cudaEvent_t ev_copy[12] = {};
+    cudaEvent_t ev_copy[16] = {};
     // optional per-stage CUDA-event timing (bmq3d_timing_*): pairs recorded on `stream`
     bool timing = false;
     struct Span { int slot; cudaEvent_t a, b; };
@@ -298,13 +298,18 @@ int stage_error(bmq3d_solver *s, int which)
     return BMQ_OK;
 }
 
-int stage_apply(bmq3d_solver *s, int which)
+// comp >= 0 (velocity only): that component alone, so that the host-buffer path can send it home
+// while the next one is computed
+int stage_apply(bmq3d_solver *s, int which, int comp);
+int stage_apply(bmq3d_solver *s, int which) { return stage_apply(s, which, -1); }
+int stage_apply(bmq3d_solver *s, int which, int comp)
 {
     StageTimer _t(s, which == 0 ? BMQ_T_APPLY_V : BMQ_T_APPLY_S);
     const float *chi[3];
     if (which == 0) {
         map_ptrs(s, BMQ_F_VBWD_X, chi);
         for (int c = 0; c < 3; ++c) {
+            if (comp >= 0 && c != comp) continue;
             float *o = s->f[BMQ_F_U + c].vbase();
             const float *adv = s->scratch[c].vbase();
             const float *e = s->scratch[5 + c].vbase();
@@ -392,7 +397,9 @@ void decide(bmq3d_solver *s, int framenum, float dt, float vel_d2, float sca_d2)
 }
 
 // accumulate: init += 1*quad9[d_ext o psi] then += proj_coeff*quad9[d_proj o psi]  (BimocqSolver.cpp:193-196)
-int stage_accumulate(bmq3d_solver *s, int which)
+int stage_accumulate(bmq3d_solver *s, int which, int comp);
+int stage_accumulate(bmq3d_solver *s, int which) { return stage_accumulate(s, which, -1); }
+int stage_accumulate(bmq3d_solver *s, int which, int comp)
 {
     StageTimer _t(s, which == 0 ? BMQ_T_ACCUM_V : BMQ_T_ACCUM_S);
     const float *psi[3];
@@ -400,6 +407,7 @@ int stage_accumulate(bmq3d_solver *s, int which)
         map_ptrs(s, BMQ_F_VFWD_X, psi);
         const float coeff[2] = {1.f, s->proj_coeff};
         for (int c = 0; c < 3; ++c) {
+            if (comp >= 0 && c != comp) continue;
             float *t = s->f[BMQ_F_U_INIT + c].vbase();
             const float *ch[2] = {s->f[BMQ_F_DU_EXT + c].vbase(), s->f[BMQ_F_DU_PROJ + c].vbase()};
             Stag sg = stag_of(BMQ_F_U + c);
@@ -638,9 +646,9 @@ static int for_which(bmq3d_solver *s, int which, int (*fn)(bmq3d_solver *, int))
 }
 int bmq3d_stage_advect(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_advect); }
 int bmq3d_stage_error(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_error); }
-int bmq3d_stage_apply(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_apply); }
+int bmq3d_stage_apply(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, static_cast<int (*)(bmq3d_solver *, int)>(stage_apply)); }
 int bmq3d_stage_blend(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_blend); }
-int bmq3d_stage_accumulate(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, stage_accumulate); }
+int bmq3d_stage_accumulate(bmq3d_solver *s, int which) { NEED(s); return for_which(s, which, static_cast<int (*)(bmq3d_solver *, int)>(stage_accumulate)); }
 int bmq3d_stage_distortion(bmq3d_solver *s, float *vel_d2, float *scalar_d2, float *max_disp_z)
 {
     NEED(s);
@@ -799,17 +807,27 @@ int bmq3d_advect_host(bmq3d_solver *s, int framenum, float dt, float *u, float *
     }
     s->stats.n_substeps = n;
     RET_IF(stage_forward(s, dt));
-    for (int which = 0; which < 2; ++which) {
-        RET_IF(stage_advect(s, which));
-        RET_IF(stage_error(s, which));
-        RET_IF(stage_apply(s, which));
-        RET_IF(stage_blend(s, which));
-        BMQ_CK(cudaEventRecord(ev[2 + which], s->stream));
-        BMQ_CK(cudaStreamWaitEvent(s->s_d2h, ev[2 + which], 0));
-        for (int c = which == 0 ? 0 : 3; c < (which == 0 ? 3 : 5); ++c) {
-            Field &fd = s->f[BMQ_F_U + c];
-            RET_IF(d2h_field(s, fd, host[c], s->s_d2h));
+    // The two mappers' stages are independent: scalars first (their download overlaps the longer
+    // velocity stages), then the velocity, each component going home as soon as it is final.
+    RET_IF(stage_advect(s, 1));
+    RET_IF(stage_error(s, 1));
+    RET_IF(stage_apply(s, 1));
+    RET_IF(stage_blend(s, 1));
+    BMQ_CK(cudaEventRecord(ev[2], s->stream));
+    BMQ_CK(cudaStreamWaitEvent(s->s_d2h, ev[2], 0));
+    for (int c = 3; c < 5; ++c) RET_IF(d2h_field(s, s->f[BMQ_F_U + c], host[c], s->s_d2h));
+    RET_IF(stage_advect(s, 0));
+    RET_IF(stage_error(s, 0));
+    const bool blend_active = s->vel_reinit_count > 0 && s->blend != 1.0f;   // stage_blend works on all three
+    for (int c = 0; c < 3; ++c) {
+        RET_IF(stage_apply(s, 0, c));
+        if (blend_active) {
+            if (c < 2) continue;
+            RET_IF(stage_blend(s, 0));
         }
+        BMQ_CK(cudaEventRecord(ev[12 + c], s->stream));
+        BMQ_CK(cudaStreamWaitEvent(s->s_d2h, ev[12 + c], 0));
+        for (int q = blend_active ? 0 : c; q <= c; ++q) RET_IF(d2h_field(s, s->f[BMQ_F_U + q], host[q], s->s_d2h));
     }
     BMQ_CK(cudaStreamSynchronize(s->s_d2h));
     BMQ_CK(cudaStreamSynchronize(s->stream));
@@ -853,8 +871,8 @@ int bmq3d_accumulate_host(bmq3d_solver *s, int framenum, float dt, const float *
         BMQ_CK(launch_add_field(s->stream, proj.alloc, stg.alloc, proj.alloc, -1.f, nel));    // final - forced
         BMQ_CK(cudaMemcpyAsync(cur.alloc, stg.alloc, nel * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
         BMQ_CK(cudaMemsetAsync(stg.alloc, 0, nel * sizeof(float), s->stream));
+        RET_IF(stage_accumulate(s, 0, c));   // overlaps the uploads of the next components
     }
-    RET_IF(stage_accumulate(s, 0));
     for (int c = 3; c < 5; ++c) {
         Field &cur = s->f[BMQ_F_U + c], &ext = s->f[BMQ_F_DU_EXT + c], &stg = s->scratch[c];
         const size_t nel = cur.stored_elems();
