@@ -25,8 +25,8 @@
 // x = 0, and every pass writes the zero Dirichlet ring itself.  (Tried and rejected on B200: a
 // 2 x 2-cells-per-thread variant with parity-split shared planes -- 24 B instead of 40 B of shared
 // traffic per update but 128 registers, 16 warps/SM and 42 % issue utilisation: 35 % slower; two
-// cells per thread at 1024 threads: 34 % slower.  The pass is bound by the per-warp dependency
-// chain LDS -> 5 DADD -> DFMA -> DMUL per level, so it wants many warps, not more work per warp.)  Single-CTA reductions of the
+// cells per thread at 1024 threads: register spills, 34 % slower.  ncu: the pass as it stands keeps
+// the shared-memory pipe 85 % busy (profiles/r1_k_jacobi_tb_ncu_details.txt).)  Single-CTA reductions of the
 // reference (calc_max over all cells) become grid-wide ones (max is exact in any order).
 #include <algorithm>
 #include <cstdint>
