@@ -1,8 +1,8 @@
-"""Times the pressure projection (gpu_multi_grid_conjugate_gradient) on one GPU with CUDA events:
+"""TEST INFRASTRUCTURE (performance comparison; loads oracle/_ref with --ref).  Times the pressure projection (gpu_multi_grid_conjugate_gradient) on one GPU with CUDA events:
 libbimocq_b200.so, and with --ref the reference's own kernels (oracle/_ref/libref3d.so) on the
 same inputs.  Prints one JSON object.
 
-  python tools/projection_timing.py --n 256 --iters 10 --ref
+  python tests/perf_projection_timing.py --n 256 --iters 10 --ref
 
 Algorithmic bytes per PCG iteration (fp64 arrays of N0 = n^3 cells; a Jacobi sweep counted as
 read x, read b, write x; level l has N_l cells):

@@ -1,6 +1,6 @@
-"""Developer tool: CUDA-event timing of every stage of one BiMocq^2 advection step (handle API),
+"""TEST INFRASTRUCTURE (performance comparison; loads oracle/_ref with --ref).  CUDA-event timing of every stage of one BiMocq^2 advection step (handle API),
 and of the reference's own kernels (oracle/_ref/libref3d.so) on the same data for comparison.
-Usage: python tools/stage_timing.py [n=256] [--ref]"""
+Usage: python tests/perf_stage_timing.py [n=256] [--ref]"""
 import ctypes as C
 import json
 import os

@@ -3,7 +3,7 @@
 n=${1:-512}
 for so in gpufluidsimulation_b200/lib/libbimocq_b200.so gpufluidsimulation_b200/lib/variants/*.so; do
   echo "== $so"
-  BMQ_LIB=$PWD/$so python tools/stage_timing.py $n 2>&1 | python -c "
+  BMQ_LIB=$PWD/$so python tests/perf_stage_timing.py $n 2>&1 | python -c "
 import sys,json
 t=sys.stdin.read()
 try:
