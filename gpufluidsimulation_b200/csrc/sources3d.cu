@@ -74,6 +74,26 @@ k_add_buoyancy(float *field, const float *__restrict__ density, const float *__r
     field[index] += f;
 }
 
+// the same with four cells per thread (128-bit accesses; needs ni % 4 == 0 and 16-byte aligned bases)
+__global__ void __launch_bounds__(128)
+k_add_buoyancy4(float *field, const float *__restrict__ density, const float *__restrict__ temperature, int ni, int nj,
+                int nk, float alpha, float beta, float dt)
+{
+    const int i4 = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i4 * 4 >= ni || j >= nj || k >= nk || !(j > 0)) return;
+    const size_t index = (size_t)i4 * 4 + (size_t)ni * (j + (size_t)nj * k), index1 = index - ni;
+    const float4 d0 = *reinterpret_cast<const float4 *>(density + index), T0 = *reinterpret_cast<const float4 *>(temperature + index);
+    const float4 d1 = *reinterpret_cast<const float4 *>(density + index1), T1 = *reinterpret_cast<const float4 *>(temperature + index1);
+    float4 f = *reinterpret_cast<float4 *>(field + index);
+    // the reference's expression per lane, same contraction
+    const float ix = 0.5 * dt * (beta * (T0.x + T1.x) - alpha * (d0.x + d1.x));
+    const float iy = 0.5 * dt * (beta * (T0.y + T1.y) - alpha * (d0.y + d1.y));
+    const float iz = 0.5 * dt * (beta * (T0.z + T1.z) - alpha * (d0.z + d1.z));
+    const float iw = 0.5 * dt * (beta * (T0.w + T1.w) - alpha * (d0.w + d1.w));
+    f.x += ix; f.y += iy; f.z += iz; f.w += iw;
+    *reinterpret_cast<float4 *>(field + index) = f;
+}
+
 // diffuse_field_kernel, GPU_kernel.cu:834-853: one Jacobi sweep of (I - coef Lap) x = field
 __global__ void __launch_bounds__(128)
 k_diffuse(const float *__restrict__ field, const float *__restrict__ in, float *out, int ni, int nj, int nk, float coef)
@@ -246,7 +266,9 @@ void gpu_emit_smoke(float *u, float *v, float *w, float *rho, float *T, float h,
 void gpu_add_buoyancy(float *field, float *density, float *temperature, int ni, int nj, int nk, float alpha, float beta, float dt)
 {
     if (!bmq::require_device()) return;
-    k_add_buoyancy<<<sgrd(ni, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt);
+    const bool vec = ni % 4 == 0 && ((reinterpret_cast<uintptr_t>(field) | reinterpret_cast<uintptr_t>(density) | reinterpret_cast<uintptr_t>(temperature)) & 15) == 0;
+    if (vec) k_add_buoyancy4<<<sgrd(ni / 4, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt);
+    else k_add_buoyancy<<<sgrd(ni, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt);
     BMQ_CKV(cudaGetLastError());
 }
 
