@@ -158,6 +158,24 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local: int) -> None:
+    """Pin this rank to the CPU cores next to its GPU (NVML's ideal affinity), so that the pinned host
+    buffers of the e2e leg are allocated on the GPU's own NUMA node and every rank uses its own
+    PCIe root.  Best effort: any failure leaves the affinity alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as exc:   # noqa: BLE001
+        print(f"bench: NUMA binding skipped ({exc})", file=sys.stderr)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -165,6 +183,7 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
