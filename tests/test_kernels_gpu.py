@@ -236,14 +236,18 @@ def test_add_buoyancy(case, oracle, ours, ref, alpha, beta):
     _three_way("gpu_add_buoyancy", args, run, ours, ref, [0])
 
 
-@pytest.mark.parametrize("iters", [1, 4])
+@pytest.mark.parametrize("iters", [1, 2, 4, 7, 20])
 def test_diffuse_field(case, oracle, ours, ref, iters):
+    """field AND both scratch arrays (the reference's GPU solver reads the first one afterwards,
+    BimocqGPUSolver.cpp:167-175); the second scratch array arrives with a non-zero ring, which the
+    sweeps read on every other level and the final copy puts into `field` (GPU_kernel.cu:862-875)."""
     c = case
     f = c.fields["c"]
-    args = [f, np.zeros_like(f), np.zeros_like(f), c.ni, c.nj, c.nk, iters, 0.37]
+    stale = (0.5 * c.fields2["c"]).astype(np.float32)
+    args = [f, np.zeros_like(f), stale, c.ni, c.nj, c.nk, iters, 0.37]
     _three_way("gpu_diffuse_field", args,
                lambda a: oracle.gpu_diffuse_field(a[0], a[1], a[2], c.ni, c.nj, c.nk, iters, float(np.float32(0.37))),
-               ours, ref, [0])
+               ours, ref, [0, 1, 2])
 
 
 def test_mad(case, oracle, ours, ref):
