@@ -106,5 +106,6 @@ int bmq_copy_async(void *dst, const void *src, size_t bytes, void *stream)
 const char *bmq_version(void) { return "bimocq_b200 0.1 (sm_100a)"; }
 
 unsigned long long bmq_kernel_launch_count(void) { return bmq::kernel_launch_count(); }
+int bmq_set_pitch_specialisation(int on) { bmq::set_pitch_specialisation(on != 0); return BMQ_OK; }
 
 }  // extern "C"

@@ -293,6 +293,15 @@ k_apply_clamp(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<N
 #ifndef BMQ_WIN_MINBLOCKS
 #define BMQ_WIN_MINBLOCKS 7   // 128-thread CTAs, >= 7 per SM (<= 73 registers, no spills): best of the A/B sweep in profiles/r1_variants.txt
 #endif
+// FIX != 0: the x and y extents are the compile-time constant FIX, so that row and plane pitches of
+// every gather become immediates of the load instructions instead of 64-bit address arithmetic.
+template <int FIX> __device__ __forceinline__ Grid3 fix_grid(const Grid3 &g)
+{
+    Grid3 r = g;
+    if (FIX) { r.ni = FIX; r.nj = FIX; }
+    return r;
+}
+
 #define BMQ_STAG_SETUP                                                                             \
     constexpr int DX = STAG == 1, DY = STAG == 2, DZ = STAG == 3;                                  \
     const int fi = g.ni + DX, fj = g.nj + DY, fk = g.nk + DZ;                                      \
@@ -303,10 +312,11 @@ k_apply_clamp(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<N
     const float cx = fmaf(h, (float)i, ox), cy = fmaf(h, (float)j, oy), cz = fmaf(h, (float)k, oz); \
     const int idx = i + fi * (j + fj * k);
 
-template <bool P2, int STAG, int NF>
+template <bool P2, int STAG, int NF, int FIX = 0>
 __global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
-k_advect_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
+k_advect_win(Grid3 g_, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> init, Map3 chi)
 {
+    const Grid3 g = fix_grid<FIX>(g_);
     BMQ_STAG_SETUP
     if (!(2 + DX < i && i < fi - 3 && 2 + DY < j && j < fj - 3 && 2 + DZ < k && k < fk - 3)) return;
     float sum[NF], val[NF], wgt[NF];
@@ -318,10 +328,11 @@ k_advect_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> in
     for (int f = 0; f < NF; ++f) out.p[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]);
 }
 
-template <bool P2, int STAG, int NF>
+template <bool P2, int STAG, int NF, int FIX = 0>
 __global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
-k_error_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
+k_error_win(Grid3 g_, int kbeg, int kend_, FieldSetRW<NF> e0, FieldSetRO<NF> src, FieldSetRO<NF> init, Map3 psi)
 {
+    const Grid3 g = fix_grid<FIX>(g_);
     BMQ_STAG_SETUP
     if (!(1 + DX < i && i < fi - 2 && 1 + DY < j && j < fj - 2 && 1 + DZ < k && k < fk - 2)) return;
     float sum[NF], val[NF], wgt[NF];
@@ -333,10 +344,11 @@ k_error_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> e0, FieldSetRO<NF> src,
     for (int f = 0; f < NF; ++f) e0.p[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]) - __ldg(init.p[f] + idx);
 }
 
-template <bool P2, int STAG, int NF, int NCH>
+template <bool P2, int STAG, int NF, int NCH, int FIX = 0>
 __global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
-k_cumulate_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change, Coeffs<NCH> coeff, Map3 map)
+k_cumulate_win(Grid3 g_, int kbeg, int kend_, FieldSetRW<NF> target, FieldSetRO<NF * NCH> change, Coeffs<NCH> coeff, Map3 map)
 {
+    const Grid3 g = fix_grid<FIX>(g_);
     BMQ_STAG_SETUP
     if (!(1 + DX < i && i < fi - 2 && 1 + DY < j && j < fj - 2 && 1 + DZ < k && k < fk - 2)) return;
     float sum[NF * NCH], val[NF * NCH], wgt[NF * NCH];
@@ -358,10 +370,11 @@ k_cumulate_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> target, FieldSetRO<N
     }
 }
 
-template <bool P2, int STAG, int NF>
+template <bool P2, int STAG, int NF, int FIX = 0>
 __global__ void __launch_bounds__(32 * BMQ_BY * BMQ_BZ, BMQ_WIN_MINBLOCKS)
-k_apply_clamp_win(Grid3 g, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> fadv, FieldSetRO<NF> e0, Map3 chi)
+k_apply_clamp_win(Grid3 g_, int kbeg, int kend_, FieldSetRW<NF> out, FieldSetRO<NF> fadv, FieldSetRO<NF> e0, Map3 chi)
 {
+    const Grid3 g = fix_grid<FIX>(g_);
     BMQ_STAG_SETUP
     float r[NF];
 #pragma unroll
@@ -641,14 +654,19 @@ cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u,
 
 // dispatch helpers: STAG (compile time) from the runtime staggering
 static inline int stag_id(Stag st) { return st.dx ? 1 : st.dy ? 2 : st.dz ? 3 : 0; }
+#define BMQ_FIXN 512   /* grids with ni == nj == BMQ_FIXN and power-of-two h get pitch-specialised kernels */
+static std::atomic<bool> g_pitch_spec{true};
+void set_pitch_specialisation(bool on) { g_pitch_spec.store(on); }
+static inline bool fixn_ok(const Grid3 &g) { return g_pitch_spec.load(std::memory_order_relaxed) && g.ni == BMQ_FIXN && g.nj == BMQ_FIXN; }
 #define DISPATCH_STAG_P2(g, st, KERNEL, NFLIST, ...)                                            \
     do {                                                                                        \
         const bool p2_ = is_pow2_h(g);                                                          \
+        const bool fx_ = p2_ && fixn_ok(g);                           \
         switch (stag_id(st)) {                                                                  \
-        case 0: if (p2_) KERNEL<true, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
-        case 1: if (p2_) KERNEL<true, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
-        case 2: if (p2_) KERNEL<true, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
-        default: if (p2_) KERNEL<true, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 0: if (fx_) KERNEL<true, 0, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 1: if (fx_) KERNEL<true, 1, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 2: if (fx_) KERNEL<true, 2, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        default: if (fx_) KERNEL<true, 3, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         }                                                                                       \
     } while (0)
 #define COMMA ,
@@ -676,7 +694,8 @@ cudaError_t launch_semilag(cudaStream_t s, const Grid3 &g, KRange r, Stag st, co
 static void k_dispatch_centred2_advect(cudaStream_t s, const Grid3 &g, KRange r, dim3 gr, dim3 bl, float *const *out,
                                        const float *const *init, Map3 m)
 {
-    if (is_pow2_h(g)) k_advect_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
+    if (is_pow2_h(g) && fixn_ok(g)) k_advect_win<true, 0, 2, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
+        else if (is_pow2_h(g)) k_advect_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
     else k_advect_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
 }
 
@@ -711,6 +730,7 @@ cudaError_t launch_error(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1) DISPATCH_STAG_P2(g, st, k_error_win, 1, g, r.kbeg, r.kend, rw<1>(e0), ro<1>(src), ro<1>(init), m);
+        else if (is_pow2_h(g) && fixn_ok(g)) k_error_win<true, 0, 2, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
         else if (is_pow2_h(g)) k_error_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
         else k_error_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
         count_launch();
@@ -742,7 +762,8 @@ cudaError_t launch_cumulate(cudaStream_t s, const Grid3 &g, KRange r, Stag st, b
             DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 2, g, r.kbeg, r.kend, rw<1>(target), ro<2>(change), c, m);
         } else if (nf == 2 && nch == 1) {
             Coeffs<1> c; c.c[0] = coeff[0];
-            if (is_pow2_h(g)) k_cumulate_win<true, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
+            if (is_pow2_h(g) && fixn_ok(g)) k_cumulate_win<true, 0, 2, 1, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
+        else if (is_pow2_h(g)) k_cumulate_win<true, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
             else k_cumulate_win<false, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
         } else return cudaErrorInvalidValue;
         count_launch();
@@ -773,6 +794,7 @@ cudaError_t launch_apply_clamp(cudaStream_t s, const Grid3 &g, KRange r, Stag st
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1) DISPATCH_STAG_P2(g, st, k_apply_clamp_win, 1, g, r.kbeg, r.kend, rw<1>(out), ro<1>(fadv), ro<1>(e0), m);
+        else if (is_pow2_h(g) && fixn_ok(g)) k_apply_clamp_win<true, 0, 2, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
         else if (is_pow2_h(g)) k_apply_clamp_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
         else k_apply_clamp_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
         count_launch();

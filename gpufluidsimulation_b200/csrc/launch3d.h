@@ -27,6 +27,7 @@ namespace bmq {
 
 Grid3 make_grid(int ni, int nj, int nk, float h);
 unsigned long long kernel_launch_count();
+void set_pitch_specialisation(bool on);   // testing knob, see bmq_set_pitch_specialisation
 
 cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float *u, const float *v,
                            const float *w, int nmap, float *const maps[][3], float cfldt, float dt);

@@ -80,3 +80,41 @@ def test_uniform_translation_at_256(cuda):
         assert float((b + U[c] * dt).abs().max()) <= 1e-7
     s.close()
     torch.cuda.empty_cache()
+
+
+def test_pitch_specialised_kernels_equal_generic_kernels():
+    """Grids with 512 x 512 planes (and a power-of-two cell size) run gather kernels whose pitches are
+    compile-time constants.  Same arithmetic: every field must be bit-identical to the generic kernels
+    (switched by the testing knob bmq_set_pitch_specialisation)."""
+    import torch
+
+    from gpufluidsimulation_b200 import capi, scenes
+    from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
+
+    lib = capi.load_library()
+    ni, nj, nk, dt = 512, 512, 24, 0.01
+    h = 1.0 / ni
+    dev = torch.device("cuda:0")
+    u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0, xp=torch, device=dev)
+    u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
+    results = []
+    try:
+        for on in (1, 0):
+            lib.bmq_set_pitch_specialisation(on)
+            s = BimocqAdvection3D(ni, nj, nk, h, 0.5)
+            s.set_initial_device(u, v, w, rho, T)
+            for frame in range(4):
+                s.advect(frame, dt)
+                s.apply_buoyancy(0.2, dt)
+                s.accumulate(frame, dt)
+            results.append({n: s.field(n).clone() for n in ("U", "V", "W", "RHO", "T", "U_INIT", "W_INIT", "RHO_INIT", "U_PREV")})
+            results[-1]["stats"] = s.stats()
+            s.close()
+    finally:
+        lib.bmq_set_pitch_specialisation(1)
+    a, b = results
+    assert a["stats"] == b["stats"]
+    for n in a:
+        if n != "stats":
+            assert torch.equal(a[n], b[n]), n
+    assert a["U"].abs().max().item() > 0
