@@ -57,12 +57,22 @@ static inline dim3 grid3(int fi, int fj, KRange r)
     if (i >= (fi) || j >= (fj) || k >= kend_) return;
 
 // ------------------------------------------------------------------ forward map (a4)
+// FIX != 0: the x and y extents are the compile-time constant FIX, so that row and plane pitches of
+// every gather become immediates of the load instructions instead of 64-bit address arithmetic.
+template <int FIX> __device__ __forceinline__ Grid3 fix_grid(const Grid3 &g)
+{
+    Grid3 r = g;
+    if (FIX) { r.ni = FIX; r.nj = FIX; }
+    return r;
+}
+
 // forward_kernel, GPU_kernel.cu:127-144: psi <- trace(psi, +dt) in place, NMAP mappers at once
 // (each mapper's particle is independent; tracing two per thread doubles the loads in flight).
-template <bool P2, int NMAP>
+template <bool P2, int NMAP, int FIX = 0>
 __global__ void __launch_bounds__(256)
-k_forward(Grid3 g, int kbeg, int kend_, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
+k_forward(Grid3 g_, int kbeg, int kend_, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
 {
+    const Grid3 g = fix_grid<FIX>(g_);
     BMQ_IJK(g.ni, g.nj)
     if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
     const int idx = i + g.ni * (j + g.nj * k);
@@ -90,10 +100,11 @@ __device__ __forceinline__ float dmc_axis(float p, float v, float a, float s)
     return (fabs(a) > 1e-4) ? p - (1 - exp(-a * s)) * v / a : p - v * s;
 }
 
-template <bool P2, int NMAP>
+template <bool P2, int NMAP, int FIX = 0>
 __global__ void __launch_bounds__(256)
-k_dmc(Grid3 g, int kbeg, int kend_, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
+k_dmc(Grid3 g_, int kbeg, int kend_, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
 {
+    const Grid3 g = fix_grid<FIX>(g_);
     BMQ_IJK(g.ni, g.nj)
     if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
     const int idx = i + g.ni * (j + g.nj * k);
@@ -293,15 +304,6 @@ k_apply_clamp(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW<N
 #ifndef BMQ_WIN_MINBLOCKS
 #define BMQ_WIN_MINBLOCKS 7   // 128-thread CTAs, >= 7 per SM (<= 73 registers, no spills): best of the A/B sweep in profiles/r1_variants.txt
 #endif
-// FIX != 0: the x and y extents are the compile-time constant FIX, so that row and plane pitches of
-// every gather become immediates of the load instructions instead of 64-bit address arithmetic.
-template <int FIX> __device__ __forceinline__ Grid3 fix_grid(const Grid3 &g)
-{
-    Grid3 r = g;
-    if (FIX) { r.ni = FIX; r.nj = FIX; }
-    return r;
-}
-
 #define BMQ_STAG_SETUP                                                                             \
     constexpr int DX = STAG == 1, DY = STAG == 2, DZ = STAG == 3;                                  \
     const int fi = g.ni + DX, fj = g.nj + DY, fk = g.nk + DZ;                                      \
@@ -480,11 +482,12 @@ k_double_advect(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW
 // estimate_kernel, GPU_kernel.cu:501-537, for NMAP mappers, with the max-reduction the
 // reference does on the host (Mapping.cpp:100-117) fused in: warp shuffle -> block -> one
 // atomicMax per block.  Also reduces max |map_z - z| (in world units) for halo sizing.
-template <bool P2, int NMAP>
+template <bool P2, int NMAP, int FIX = 0>
 __global__ void __launch_bounds__(256)
-k_estimate(Grid3 g, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
+k_estimate(Grid3 g_, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
            const signed char *__restrict__ boundary)
 {
+    const Grid3 g = fix_grid<FIX>(g_);
     const int i = blockIdx.x * 32 + threadIdx.x;
     const int j = blockIdx.y * BMQ_BY + threadIdx.y;
     const int k = kbeg + blockIdx.z * BMQ_BZ + threadIdx.z;
@@ -603,6 +606,26 @@ __global__ void __launch_bounds__(256) k_identity(Grid3 g, int kbeg, int kend_, 
 }
 
 // ================================================================== host launchers
+// Pitch specialisation: cubic-plane grids (ni == nj in {128, 256, 512}, the BASELINE sizes) with a
+// power-of-two cell size run kernels whose x and y extents are compile-time constants (fix_grid).
+static std::atomic<bool> g_pitch_spec{true};
+void set_pitch_specialisation(bool on) { g_pitch_spec.store(on); }
+static inline int fix_of(const Grid3 &g)
+{
+    if (!g_pitch_spec.load(std::memory_order_relaxed) || g.ni != g.nj) return 0;
+    return (g.ni == 512 || g.ni == 256 || g.ni == 128) ? g.ni : 0;
+}
+#define DISPATCH_P2_FIX(g, KERNEL, NM, ...)                                                     \
+    do {                                                                                        \
+        if (!is_pow2_h(g)) { KERNEL<false, NM><<<gr, bl, 0, s>>>(__VA_ARGS__); break; }         \
+        switch (fix_of(g)) {                                                                    \
+        case 512: KERNEL<true, NM, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                       \
+        case 256: KERNEL<true, NM, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                       \
+        case 128: KERNEL<true, NM, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                       \
+        default: KERNEL<true, NM><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                        \
+        }                                                                                       \
+    } while (0)
+
 #define DISPATCH_P2(g, CALL_T, CALL_F) do { if (is_pow2_h(g)) { CALL_T; } else { CALL_F; } } while (0)
 
 cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float *u, const float *v,
@@ -613,13 +636,11 @@ cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float
     dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
     if (nmap == 1) {
         MapSetRW<1> m; m.x[0] = maps[0][0]; m.y[0] = maps[0][1]; m.z[0] = maps[0][2];
-        DISPATCH_P2(g, (k_forward<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)),
-                    (k_forward<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)));
+        DISPATCH_P2_FIX(g, k_forward, 1, g, r.kbeg, r.kend, vel, m, cfldt, dt);
     } else {
         MapSetRW<2> m;
         for (int q = 0; q < 2; ++q) { m.x[q] = maps[q][0]; m.y[q] = maps[q][1]; m.z[q] = maps[q][2]; }
-        DISPATCH_P2(g, (k_forward<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)),
-                    (k_forward<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, m, cfldt, dt)));
+        DISPATCH_P2_FIX(g, k_forward, 2, g, r.kbeg, r.kend, vel, m, cfldt, dt);
     }
     count_launch();
     return cudaGetLastError();
@@ -636,16 +657,14 @@ cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u,
         MapSetRO<1> a; MapSetRW<1> b;
         a.x[0] = in[0][0]; a.y[0] = in[0][1]; a.z[0] = in[0][2];
         b.x[0] = out[0][0]; b.y[0] = out[0][1]; b.z[0] = out[0][2];
-        DISPATCH_P2(g, (k_dmc<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)),
-                    (k_dmc<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)));
+        DISPATCH_P2_FIX(g, k_dmc, 1, g, r.kbeg, r.kend, vel, a, b, substep);
     } else {
         MapSetRO<2> a; MapSetRW<2> b;
         for (int q = 0; q < 2; ++q) {
             a.x[q] = in[q][0]; a.y[q] = in[q][1]; a.z[q] = in[q][2];
             b.x[q] = out[q][0]; b.y[q] = out[q][1]; b.z[q] = out[q][2];
         }
-        DISPATCH_P2(g, (k_dmc<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)),
-                    (k_dmc<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, vel, a, b, substep)));
+        DISPATCH_P2_FIX(g, k_dmc, 2, g, r.kbeg, r.kend, vel, a, b, substep);
     }
     count_launch();
     return cudaGetLastError();
@@ -654,19 +673,32 @@ cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u,
 
 // dispatch helpers: STAG (compile time) from the runtime staggering
 static inline int stag_id(Stag st) { return st.dx ? 1 : st.dy ? 2 : st.dz ? 3 : 0; }
-#define BMQ_FIXN 512   /* grids with ni == nj == BMQ_FIXN and power-of-two h get pitch-specialised kernels */
-static std::atomic<bool> g_pitch_spec{true};
-void set_pitch_specialisation(bool on) { g_pitch_spec.store(on); }
-static inline bool fixn_ok(const Grid3 &g) { return g_pitch_spec.load(std::memory_order_relaxed) && g.ni == BMQ_FIXN && g.nj == BMQ_FIXN; }
 #define DISPATCH_STAG_P2(g, st, KERNEL, NFLIST, ...)                                            \
     do {                                                                                        \
-        const bool p2_ = is_pow2_h(g);                                                          \
-        const bool fx_ = p2_ && fixn_ok(g);                           \
-        switch (stag_id(st)) {                                                                  \
-        case 0: if (fx_) KERNEL<true, 0, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
-        case 1: if (fx_) KERNEL<true, 1, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
-        case 2: if (fx_) KERNEL<true, 2, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
-        default: if (fx_) KERNEL<true, 3, NFLIST, BMQ_FIXN><<<gr, bl, 0, s>>>(__VA_ARGS__); else if (p2_) KERNEL<true, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); else KERNEL<false, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        const int fx_ = is_pow2_h(g) ? fix_of(g) : 0;                                           \
+        const int key_ = (is_pow2_h(g) ? 4 : 0) + stag_id(st);                                  \
+        switch (fx_ * 8 + key_) {                                                               \
+        case 512 * 8 + 4 + 0: KERNEL<true, 0, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 4 + 0: KERNEL<true, 0, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 4 + 0: KERNEL<true, 0, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 4 + 0: KERNEL<true, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 0: KERNEL<false, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 512 * 8 + 4 + 1: KERNEL<true, 1, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 4 + 1: KERNEL<true, 1, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 4 + 1: KERNEL<true, 1, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 4 + 1: KERNEL<true, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 1: KERNEL<false, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 512 * 8 + 4 + 2: KERNEL<true, 2, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 4 + 2: KERNEL<true, 2, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 4 + 2: KERNEL<true, 2, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 4 + 2: KERNEL<true, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 2: KERNEL<false, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 512 * 8 + 4 + 3: KERNEL<true, 3, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 4 + 3: KERNEL<true, 3, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 4 + 3: KERNEL<true, 3, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 4 + 3: KERNEL<true, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 3: KERNEL<false, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        default: break;                                                                         \
         }                                                                                       \
     } while (0)
 #define COMMA ,
@@ -694,9 +726,7 @@ cudaError_t launch_semilag(cudaStream_t s, const Grid3 &g, KRange r, Stag st, co
 static void k_dispatch_centred2_advect(cudaStream_t s, const Grid3 &g, KRange r, dim3 gr, dim3 bl, float *const *out,
                                        const float *const *init, Map3 m)
 {
-    if (is_pow2_h(g) && fixn_ok(g)) k_advect_win<true, 0, 2, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
-        else if (is_pow2_h(g)) k_advect_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
-    else k_advect_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
+    DISPATCH_STAG_P2(g, (Stag{0, 0, 0}), k_advect_win, 2, g, r.kbeg, r.kend, rw<2>(out), ro<2>(init), m);
 }
 
 cudaError_t launch_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
@@ -730,9 +760,7 @@ cudaError_t launch_error(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1) DISPATCH_STAG_P2(g, st, k_error_win, 1, g, r.kbeg, r.kend, rw<1>(e0), ro<1>(src), ro<1>(init), m);
-        else if (is_pow2_h(g) && fixn_ok(g)) k_error_win<true, 0, 2, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
-        else if (is_pow2_h(g)) k_error_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
-        else k_error_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
+        else DISPATCH_STAG_P2(g, (Stag{0, 0, 0}), k_error_win, 2, g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
         count_launch();
         return cudaGetLastError();
     }
@@ -762,9 +790,7 @@ cudaError_t launch_cumulate(cudaStream_t s, const Grid3 &g, KRange r, Stag st, b
             DISPATCH_STAG_P2(g, st, k_cumulate_win, 1 COMMA 2, g, r.kbeg, r.kend, rw<1>(target), ro<2>(change), c, m);
         } else if (nf == 2 && nch == 1) {
             Coeffs<1> c; c.c[0] = coeff[0];
-            if (is_pow2_h(g) && fixn_ok(g)) k_cumulate_win<true, 0, 2, 1, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
-        else if (is_pow2_h(g)) k_cumulate_win<true, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
-            else k_cumulate_win<false, 0, 2, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
+            DISPATCH_STAG_P2(g, (Stag{0, 0, 0}), k_cumulate_win, 2 COMMA 1, g, r.kbeg, r.kend, rw<2>(target), ro<2>(change), c, m);
         } else return cudaErrorInvalidValue;
         count_launch();
         return cudaGetLastError();
@@ -794,9 +820,7 @@ cudaError_t launch_apply_clamp(cudaStream_t s, const Grid3 &g, KRange r, Stag st
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1) DISPATCH_STAG_P2(g, st, k_apply_clamp_win, 1, g, r.kbeg, r.kend, rw<1>(out), ro<1>(fadv), ro<1>(e0), m);
-        else if (is_pow2_h(g) && fixn_ok(g)) k_apply_clamp_win<true, 0, 2, BMQ_FIXN><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
-        else if (is_pow2_h(g)) k_apply_clamp_win<true, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
-        else k_apply_clamp_win<false, 0, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
+        else DISPATCH_STAG_P2(g, (Stag{0, 0, 0}), k_apply_clamp_win, 2, g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);
         count_launch();
         return cudaGetLastError();
     }
@@ -847,8 +871,7 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
         b.x[0] = bwd[0][0]; b.y[0] = bwd[0][1]; b.z[0] = bwd[0][2];
         f.x[0] = fwd[0][0]; f.y[0] = fwd[0][1]; f.z[0] = fwd[0][2];
         o.dist[0] = dist ? dist[0] : nullptr; o.d2max[0] = d2max ? d2max[0] : nullptr; o.dispz = dispz;
-        DISPATCH_P2(g, (k_estimate<true, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)),
-                    (k_estimate<false, 1><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)));
+        DISPATCH_P2_FIX(g, k_estimate, 1, g, r.kbeg, r.kend, b, f, o, boundary);
     } else {
         MapSetRO<2> b, f; DistOut<2> o;
         for (int q = 0; q < 2; ++q) {
@@ -857,8 +880,7 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
             o.dist[q] = dist ? dist[q] : nullptr; o.d2max[q] = d2max ? d2max[q] : nullptr;
         }
         o.dispz = dispz;
-        DISPATCH_P2(g, (k_estimate<true, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)),
-                    (k_estimate<false, 2><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, b, f, o, boundary)));
+        DISPATCH_P2_FIX(g, k_estimate, 2, g, r.kbeg, r.kend, b, f, o, boundary);
     }
     count_launch();
     return cudaGetLastError();

@@ -45,9 +45,9 @@ int bmq_clear_error(void);
 const char *bmq_version(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 unsigned long long bmq_kernel_launch_count(void);
-/* Testing knob.  Grids with ni == nj == 512 and a power-of-two cell size run gather kernels whose row
- * and plane pitches are compile-time constants (same arithmetic, 17 % fewer instructions); 0 switches
- * them off so that tests can compare the two paths bit for bit.  Default: on. */
+/* Testing knob.  Grids with ni == nj in {128, 256, 512} and a power-of-two cell size run kernels whose
+ * row and plane pitches are compile-time constants (same arithmetic, 17 % fewer instructions); 0
+ * switches them off so that tests can compare the two paths bit for bit.  Default: on. */
 int bmq_set_pitch_specialisation(int on);
 
 /* ---- peer-memory plumbing for the z-slab halo exchange over NVLink (one process per GPU).

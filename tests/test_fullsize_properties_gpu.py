@@ -82,18 +82,20 @@ def test_uniform_translation_at_256(cuda):
     torch.cuda.empty_cache()
 
 
-def test_pitch_specialised_kernels_equal_generic_kernels():
-    """Grids with 512 x 512 planes (and a power-of-two cell size) run gather kernels whose pitches are
-    compile-time constants.  Same arithmetic: every field must be bit-identical to the generic kernels
-    (switched by the testing knob bmq_set_pitch_specialisation)."""
+@pytest.mark.parametrize("n", [512, 256, 128])
+def test_pitch_specialised_kernels_equal_generic_kernels(n):
+    """Grids with n x n planes, n in {128, 256, 512} (and a power-of-two cell size) run kernels whose
+    pitches are compile-time constants.  Same arithmetic: every field and map must be bit-identical to
+    the generic kernels (switched by the testing knob bmq_set_pitch_specialisation)."""
     import torch
 
     from gpufluidsimulation_b200 import capi, scenes
     from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
 
     lib = capi.load_library()
-    ni, nj, nk, dt = 512, 512, 24, 0.01
+    ni, nj, nk = n, n, 24
     h = 1.0 / ni
+    dt = 0.01 * 512 / n
     dev = torch.device("cuda:0")
     u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0, xp=torch, device=dev)
     u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
@@ -107,14 +109,15 @@ def test_pitch_specialised_kernels_equal_generic_kernels():
                 s.advect(frame, dt)
                 s.apply_buoyancy(0.2, dt)
                 s.accumulate(frame, dt)
-            results.append({n: s.field(n).clone() for n in ("U", "V", "W", "RHO", "T", "U_INIT", "W_INIT", "RHO_INIT", "U_PREV")})
+            results.append({f: s.field(f).clone() for f in ("U", "V", "W", "RHO", "T", "U_INIT", "W_INIT", "RHO_INIT", "U_PREV",
+                                                            "VBWD_X", "VFWD_Z", "SBWD_Y", "SFWD_X")})
             results[-1]["stats"] = s.stats()
             s.close()
     finally:
         lib.bmq_set_pitch_specialisation(1)
     a, b = results
     assert a["stats"] == b["stats"]
-    for n in a:
-        if n != "stats":
-            assert torch.equal(a[n], b[n]), n
+    for f in a:
+        if f != "stats":
+            assert torch.equal(a[f], b[f]), f
     assert a["U"].abs().max().item() > 0
