@@ -15,10 +15,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CHECK = zslab.CUR + zslab.INIT + zslab.PREV + zslab.MAPS_BWD + zslab.MAPS_FWD + zslab.MAPS_BWDP
 
 
-@pytest.mark.parametrize("world,blend,L", [(2, 1.0, 1.0), (3, 0.5, 0.2), (4, 1.0, 1.0)])
-def test_logical_slabs_on_one_gpu_match_single_solver(cuda, world, blend, L):
+# the last case has 128 x 128 planes and a power-of-two cell size: the pitch-specialised kernels on slabs
+@pytest.mark.parametrize("world,blend,L,dims", [(2, 1.0, 1.0, (32, 28, 48)), (3, 0.5, 0.2, (32, 28, 48)), (4, 1.0, 1.0, (32, 28, 48)),
+                                                (2, 0.5, 1.0, (128, 128, 40))])
+def test_logical_slabs_on_one_gpu_match_single_solver(cuda, world, blend, L, dims):
     from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
-    ni, nj, nk, halo, frames, dt = 32, 28, 48, 11, 6, 0.02
+    (ni, nj, nk), halo, frames, dt = dims, 11, 6, 0.02
+    if ni == 128:
+        frames, dt = 4, 0.005
     h = L / ni
     u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, L)
     u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
