@@ -606,8 +606,8 @@ __global__ void __launch_bounds__(256) k_identity(Grid3 g, int kbeg, int kend_, 
 }
 
 // ================================================================== host launchers
-// Pitch specialisation: cubic-plane grids (ni == nj in {128, 256, 512}, the BASELINE sizes) with a
-// power-of-two cell size run kernels whose x and y extents are compile-time constants (fix_grid).
+// Pitch specialisation: cubic-plane grids (ni == nj in {128, 256, 512}, the BASELINE sizes) run
+// kernels whose x and y extents are compile-time constants (fix_grid).
 static std::atomic<bool> g_pitch_spec{true};
 void set_pitch_specialisation(bool on) { g_pitch_spec.store(on); }
 static inline int fix_of(const Grid3 &g)
@@ -617,12 +617,15 @@ static inline int fix_of(const Grid3 &g)
 }
 #define DISPATCH_P2_FIX(g, KERNEL, NM, ...)                                                     \
     do {                                                                                        \
-        if (!is_pow2_h(g)) { KERNEL<false, NM><<<gr, bl, 0, s>>>(__VA_ARGS__); break; }         \
-        switch (fix_of(g)) {                                                                    \
-        case 512: KERNEL<true, NM, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                       \
-        case 256: KERNEL<true, NM, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                       \
-        case 128: KERNEL<true, NM, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                       \
-        default: KERNEL<true, NM><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                        \
+        switch (fix_of(g) * 2 + (is_pow2_h(g) ? 1 : 0)) {                                       \
+        case 512 * 2 + 1: KERNEL<true, NM, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break;               \
+        case 512 * 2: KERNEL<false, NM, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                  \
+        case 256 * 2 + 1: KERNEL<true, NM, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break;               \
+        case 256 * 2: KERNEL<false, NM, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                  \
+        case 128 * 2 + 1: KERNEL<true, NM, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break;               \
+        case 128 * 2: KERNEL<false, NM, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                  \
+        case 1: KERNEL<true, NM><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                         \
+        default: KERNEL<false, NM><<<gr, bl, 0, s>>>(__VA_ARGS__); break;                       \
         }                                                                                       \
     } while (0)
 
@@ -675,27 +678,38 @@ cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u,
 static inline int stag_id(Stag st) { return st.dx ? 1 : st.dy ? 2 : st.dz ? 3 : 0; }
 #define DISPATCH_STAG_P2(g, st, KERNEL, NFLIST, ...)                                            \
     do {                                                                                        \
-        const int fx_ = is_pow2_h(g) ? fix_of(g) : 0;                                           \
         const int key_ = (is_pow2_h(g) ? 4 : 0) + stag_id(st);                                  \
-        switch (fx_ * 8 + key_) {                                                               \
+        switch (fix_of(g) * 8 + key_) {                                                         \
         case 512 * 8 + 4 + 0: KERNEL<true, 0, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 512 * 8 + 0: KERNEL<false, 0, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 256 * 8 + 4 + 0: KERNEL<true, 0, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 0: KERNEL<false, 0, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 128 * 8 + 4 + 0: KERNEL<true, 0, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 0: KERNEL<false, 0, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 4 + 0: KERNEL<true, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 0: KERNEL<false, 0, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 512 * 8 + 4 + 1: KERNEL<true, 1, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 512 * 8 + 1: KERNEL<false, 1, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 256 * 8 + 4 + 1: KERNEL<true, 1, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 1: KERNEL<false, 1, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 128 * 8 + 4 + 1: KERNEL<true, 1, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 1: KERNEL<false, 1, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 4 + 1: KERNEL<true, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 1: KERNEL<false, 1, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 512 * 8 + 4 + 2: KERNEL<true, 2, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 512 * 8 + 2: KERNEL<false, 2, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 256 * 8 + 4 + 2: KERNEL<true, 2, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 2: KERNEL<false, 2, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 128 * 8 + 4 + 2: KERNEL<true, 2, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 2: KERNEL<false, 2, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 4 + 2: KERNEL<true, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 2: KERNEL<false, 2, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 512 * 8 + 4 + 3: KERNEL<true, 3, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 512 * 8 + 3: KERNEL<false, 3, NFLIST, 512><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 256 * 8 + 4 + 3: KERNEL<true, 3, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 256 * 8 + 3: KERNEL<false, 3, NFLIST, 256><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 128 * 8 + 4 + 3: KERNEL<true, 3, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
+        case 128 * 8 + 3: KERNEL<false, 3, NFLIST, 128><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 4 + 3: KERNEL<true, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         case 3: KERNEL<false, 3, NFLIST><<<gr, bl, 0, s>>>(__VA_ARGS__); break; \
         default: break;                                                                         \

@@ -45,7 +45,7 @@ int bmq_clear_error(void);
 const char *bmq_version(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 unsigned long long bmq_kernel_launch_count(void);
-/* Testing knob.  Grids with ni == nj in {128, 256, 512} and a power-of-two cell size run kernels whose
+/* Testing knob.  Grids with ni == nj in {128, 256, 512} run kernels whose
  * row and plane pitches are compile-time constants (same arithmetic, 17 % fewer instructions); 0
  * switches them off so that tests can compare the two paths bit for bit.  Default: on. */
 int bmq_set_pitch_specialisation(int on);

@@ -82,9 +82,9 @@ def test_uniform_translation_at_256(cuda):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("n", [512, 256, 128])
-def test_pitch_specialised_kernels_equal_generic_kernels(n):
-    """Grids with n x n planes, n in {128, 256, 512} (and a power-of-two cell size) run kernels whose
+@pytest.mark.parametrize("n,L", [(512, 1.0), (256, 1.0), (128, 1.0), (256, 0.2), (128, 0.2)])
+def test_pitch_specialised_kernels_equal_generic_kernels(n, L):
+    """Grids with n x n planes, n in {128, 256, 512} (cell size a power of two or, L = 0.2, not) run kernels whose
     pitches are compile-time constants.  Same arithmetic: every field and map must be bit-identical to
     the generic kernels (switched by the testing knob bmq_set_pitch_specialisation)."""
     import torch
@@ -94,10 +94,10 @@ def test_pitch_specialised_kernels_equal_generic_kernels(n):
 
     lib = capi.load_library()
     ni, nj, nk = n, n, 24
-    h = 1.0 / ni
+    h = L / ni
     dt = 0.01 * 512 / n
     dev = torch.device("cuda:0")
-    u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0, xp=torch, device=dev)
+    u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, L, xp=torch, device=dev)
     u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
     results = []
     try:
