@@ -30,13 +30,17 @@ def test_every_declared_symbol_has_a_ctypes_prototype(lib):
 
 
 def test_legacy_prototypes_match_reference_header_shapes():
-    """The 14 hot-path legacy symbols keep the reference's argument counts
-    (bimocq3D/GPU_Advection.h:26-86,97)."""
+    """All 22 `extern "C"` functions of the reference (bimocq3D/GPU_Advection.h:26-108) are declared
+    with the reference's argument counts: the 14 hot-path symbols and the 8 of SURVEY 8(f)."""
     expected = {"gpu_solve_forward": 12, "gpu_solve_backwardDMC": 14, "gpu_advect_velocity": 14,
                 "gpu_advect_vel_double": 18, "gpu_advect_field": 10, "gpu_advect_field_double": 14,
                 "gpu_accumulate_velocity": 15, "gpu_accumulate_field": 11, "gpu_estimate_distortion": 11,
                 "gpu_add": 4, "gpu_compensate_velocity": 20, "gpu_compensate_field": 14, "gpu_semilag": 14,
-                "gpu_add_field": 5}
+                "gpu_add_field": 5,
+                "gpu_emit_smoke": 16, "gpu_add_buoyancy": 9, "gpu_diffuse_field": 8, "gpu_projection_jacobi": 14,
+                "gpu_clamp_extrema": 16, "gpu_mad": 6, "gpu_conjugate_gradient": 13,
+                "gpu_multi_grid_conjugate_gradient": 14}
+    assert len(expected) == 22
     text = re.sub(r"/\*.*?\*/", "", open(capi.header_path()).read(), flags=re.S)
     for name, nargs in expected.items():
         m = re.search(r"void\s+%s\s*\(([^)]*)\)" % name, text)
