@@ -49,7 +49,8 @@ _H = C.c_void_p  # bmq3d_solver*
 class Stats3D(C.Structure):
     _fields_ = [("max_v", _f), ("cfldt", _f), ("n_substeps", _I), ("vel_distortion", _f),
                 ("scalar_distortion", _f), ("vel_reinit", _I), ("scalar_reinit", _I),
-                ("vel_reinit_count", _I), ("scalar_reinit_count", _I), ("max_disp_z", _f)]
+                ("vel_reinit_count", _I), ("scalar_reinit_count", _I), ("max_disp_z", _f),
+                ("max_disp_z_vel", _f), ("max_disp_z_scalar", _f)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -183,6 +184,8 @@ _PROTOS = {
     "bmq3d_stage_apply": (_I, [_H, _I]),
     "bmq3d_stage_blend": (_I, [_H, _I]),
     "bmq3d_stage_distortion": (_I, [_H, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f)]),
+    "bmq3d_stage_distortion2": (_I, [_H, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f)]),
+    "bmq3d_grow_halo": (_I, [_H, _I]),
     "bmq3d_stage_decide": (_I, [_H, _I, _f, _f, _f]),
     "bmq3d_stage_accumulate": (_I, [_H, _I]),
     "bmq3d_stage_reinit": (_I, [_H, _I, _I]),

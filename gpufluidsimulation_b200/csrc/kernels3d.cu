@@ -481,7 +481,7 @@ k_double_advect(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW
 // ------------------------------------------------------------------ distortion (a10) + reductions
 // estimate_kernel, GPU_kernel.cu:501-537, for NMAP mappers, with the max-reduction the
 // reference does on the host (Mapping.cpp:100-117) fused in: warp shuffle -> block -> one
-// atomicMax per block.  Also reduces max |map_z - z| (in world units) for halo sizing.
+// atomicMax per block.  Also reduces max |map_z - z| (in world units) per mapper for halo sizing.
 template <bool P2, int NMAP, int FIX = 0>
 __global__ void __launch_bounds__(256)
 k_estimate(Grid3 g_, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
@@ -491,9 +491,9 @@ k_estimate(Grid3 g_, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd
     const int i = blockIdx.x * 32 + threadIdx.x;
     const int j = blockIdx.y * BMQ_BY + threadIdx.y;
     const int k = kbeg + blockIdx.z * BMQ_BZ + threadIdx.z;
-    float d2[NMAP], dispz = 0.f;
+    float d2[NMAP], dispz[NMAP];
 #pragma unroll
-    for (int m = 0; m < NMAP; ++m) d2[m] = 0.f;
+    for (int m = 0; m < NMAP; ++m) d2[m] = dispz[m] = 0.f;
     const bool inside = i < g.ni && j < g.nj && k < kend_;
     if (inside && i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2) {
         const int idx = i + g.ni * (j + g.nj * k);
@@ -513,7 +513,7 @@ k_estimate(Grid3 g_, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd
             const float d = fmaxf(dbf, dfb);
             if (outp.dist[m]) outp.dist[m][idx] = d;
             if (counted) d2[m] = d;
-            dispz = fmaxf(dispz, fmaxf(fabsf(b.z - pz), fabsf(f2.z - pz)));
+            dispz[m] = fmaxf(fabsf(b.z - pz), fabsf(f2.z - pz));
         }
     }
 #pragma unroll
@@ -521,7 +521,11 @@ k_estimate(Grid3 g_, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd
         if (outp.d2max[m]) block_atomic_max(d2[m], outp.d2max[m]);
         __syncthreads();
     }
-    if (outp.dispz) block_atomic_max(dispz, outp.dispz);
+#pragma unroll
+    for (int m = 0; m < NMAP; ++m) {
+        if (outp.dispz[m]) block_atomic_max(dispz[m], outp.dispz[m]);
+        __syncthreads();
+    }
 }
 
 // max |x| over up to three arrays (getCFL, BimocqSolver.cpp:1093-1117), grid-stride, float4 loads
@@ -876,7 +880,7 @@ cudaError_t launch_double_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag 
 
 cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, const float *const bwd[][3],
                             const float *const fwd[][3], float *const *dist, float *const *d2max,
-                            float *dispz, const signed char *boundary)
+                            float *const *dispz, const signed char *boundary)
 {
     if (r.kend <= r.kbeg) return cudaSuccess;
     dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
@@ -884,7 +888,7 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
         MapSetRO<1> b, f; DistOut<1> o;
         b.x[0] = bwd[0][0]; b.y[0] = bwd[0][1]; b.z[0] = bwd[0][2];
         f.x[0] = fwd[0][0]; f.y[0] = fwd[0][1]; f.z[0] = fwd[0][2];
-        o.dist[0] = dist ? dist[0] : nullptr; o.d2max[0] = d2max ? d2max[0] : nullptr; o.dispz = dispz;
+        o.dist[0] = dist ? dist[0] : nullptr; o.d2max[0] = d2max ? d2max[0] : nullptr; o.dispz[0] = dispz ? dispz[0] : nullptr;
         DISPATCH_P2_FIX(g, k_estimate, 1, g, r.kbeg, r.kend, b, f, o, boundary);
     } else {
         MapSetRO<2> b, f; DistOut<2> o;
@@ -892,8 +896,8 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
             b.x[q] = bwd[q][0]; b.y[q] = bwd[q][1]; b.z[q] = bwd[q][2];
             f.x[q] = fwd[q][0]; f.y[q] = fwd[q][1]; f.z[q] = fwd[q][2];
             o.dist[q] = dist ? dist[q] : nullptr; o.d2max[q] = d2max ? d2max[q] : nullptr;
+            o.dispz[q] = dispz ? dispz[q] : nullptr;
         }
-        o.dispz = dispz;
         DISPATCH_P2_FIX(g, k_estimate, 2, g, r.kbeg, r.kend, b, f, o, boundary);
     }
     count_launch();

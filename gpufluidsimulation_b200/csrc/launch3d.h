@@ -16,7 +16,7 @@ template <int N> struct MapSetRW { float *x[N], *y[N], *z[N]; };
 template <int N> struct FieldSetRO { const float *p[N]; };
 template <int N> struct FieldSetRW { float *p[N]; };
 template <int N> struct Coeffs { float c[N]; };
-template <int N> struct DistOut { float *dist[N]; float *d2max[N]; float *dispz; };
+template <int N> struct DistOut { float *dist[N]; float *d2max[N]; float *dispz[N]; };
 struct IdentityOut { float *x[4], *y[4], *z[4]; };
 
 }  // namespace bmq
@@ -54,11 +54,11 @@ cudaError_t launch_clamp_extrema(cudaStream_t s, int fi, int fj, int fk, KRange 
 cudaError_t launch_double_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool is_point, int nf,
                                  float *const *field, const float *const *prev, const float *const chi[3],
                                  const float *const chip[3], float blend);
-// dist / d2max may be null (or hold null entries); dispz may be null.  d2max and dispz are
+// dist / d2max / dispz may be null (or hold null entries).  d2max and dispz (one per mapper) are
 // atomically max-ed into, so zero them first.
 cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, const float *const bwd[][3],
                             const float *const fwd[][3], float *const *dist, float *const *d2max,
-                            float *dispz, const signed char *boundary);
+                            float *const *dispz, const signed char *boundary);
 cudaError_t launch_maxabs3(cudaStream_t s, const float *a, size_t na, const float *b, size_t nb,
                            const float *c, size_t nc, float *out_dev);
 cudaError_t launch_axpy(cudaStream_t s, float *a, const float *b, float c, size_t n);

@@ -354,10 +354,11 @@ int stage_blend(bmq3d_solver *s, int which)
 }
 
 // estimateDistortion for both mappers (Mapping.cpp:91-118) with the max on the device
+// dispz[0], dispz[1]: max |map_z - z| in cells of the velocity / scalar mapper (z-slab halo sizing)
 int stage_distortion(bmq3d_solver *s, float *vel_d2, float *sca_d2, float *dispz)
 {
     StageTimer _t(s, BMQ_T_DISTORTION);
-    BMQ_CK(cudaMemsetAsync(s->d_red, 0, 4 * sizeof(float), s->stream));
+    BMQ_CK(cudaMemsetAsync(s->d_red, 0, 5 * sizeof(float), s->stream));
     const float *const b[2][3] = {
         {s->f[BMQ_F_VBWD_X].vbase(), s->f[BMQ_F_VBWD_Y].vbase(), s->f[BMQ_F_VBWD_Z].vbase()},
         {s->f[BMQ_F_SBWD_X].vbase(), s->f[BMQ_F_SBWD_Y].vbase(), s->f[BMQ_F_SBWD_Z].vbase()}};
@@ -365,12 +366,17 @@ int stage_distortion(bmq3d_solver *s, float *vel_d2, float *sca_d2, float *dispz
         {s->f[BMQ_F_VFWD_X].vbase(), s->f[BMQ_F_VFWD_Y].vbase(), s->f[BMQ_F_VFWD_Z].vbase()},
         {s->f[BMQ_F_SFWD_X].vbase(), s->f[BMQ_F_SFWD_Y].vbase(), s->f[BMQ_F_SFWD_Z].vbase()}};
     float *d2[2] = {s->d_red + 1, s->d_red + 2};
-    BMQ_CK(launch_estimate(s->stream, s->g, own(s, 0), 2, b, f, nullptr, d2, s->d_red + 3, nullptr));
-    BMQ_CK(cudaMemcpyAsync(s->h_red, s->d_red, 4 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    float *dz[2] = {s->d_red + 3, s->d_red + 4};
+    BMQ_CK(launch_estimate(s->stream, s->g, own(s, 0), 2, b, f, nullptr, d2, dz, nullptr));
+    BMQ_CK(cudaMemcpyAsync(s->h_red, s->d_red, 5 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     BMQ_CK(cudaStreamSynchronize(s->stream));
     *vel_d2 = s->h_red[1];
     *sca_d2 = s->h_red[2];
-    *dispz = s->h_red[3] / s->h;
+    dispz[0] = s->h_red[3] / s->h;
+    dispz[1] = s->h_red[4] / s->h;
+    s->stats.max_disp_z = dispz[0] > dispz[1] ? dispz[0] : dispz[1];
+    s->stats.max_disp_z_vel = dispz[0];
+    s->stats.max_disp_z_scalar = dispz[1];
     return BMQ_OK;
 }
 
@@ -523,6 +529,36 @@ int bmq3d_destroy(bmq3d_solver *s)
     return BMQ_OK;
 }
 
+// Re-allocates every field with a wider halo, keeping the stored planes where they are in the
+// global grid (new planes are zero; the next halo exchange fills them).
+int bmq3d_grow_halo(bmq3d_solver *s, int new_halo)
+{
+    NEED(s);
+    if (new_halo <= s->halo) return BMQ_OK;
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    const int old_halo = s->halo;
+    s->halo = new_halo;
+    auto regrow = [&](Field &fd, Stag st) -> int {
+        if (!fd.alloc) return BMQ_OK;
+        Field old = fd;
+        int rc = alloc_field(s, fd, st);
+        if (rc != BMQ_OK) { fd = old; return rc; }
+        BMQ_CK(cudaMemcpyAsync(fd.alloc + fd.plane() * (size_t)(old.p0 - fd.p0), old.alloc, old.stored_elems() * sizeof(float),
+                               cudaMemcpyDeviceToDevice, s->stream));
+        BMQ_CK(cudaStreamSynchronize(s->stream));
+        BMQ_CK(cudaFree(old.alloc));
+        return BMQ_OK;
+    };
+    int rc = BMQ_OK;
+    for (int id = 0; id < BMQ_F_COUNT && rc == BMQ_OK; ++id) rc = regrow(s->f[id], stag_of(id));
+    for (int q = 0; q < N_SCRATCH && rc == BMQ_OK; ++q) rc = regrow(s->scratch[q], stag_of(SCRATCH_BASE + q));
+    for (int q = 0; q < N_TMPMAP && rc == BMQ_OK; ++q) rc = regrow(s->tmpmap[q], Stag{0, 0, 0});
+    if (rc != BMQ_OK) { s->halo = old_halo; return rc; }
+    // the identity maps must hold the identity in the new halo planes as well (a reinitialised map is
+    // the identity everywhere it is stored); everything else is refreshed by its exchange
+    return BMQ_OK;
+}
+
 int bmq3d_set_stream(bmq3d_solver *s, void *stream)
 {
     NEED(s);
@@ -652,12 +688,22 @@ int bmq3d_stage_accumulate(bmq3d_solver *s, int which) { NEED(s); return for_whi
 int bmq3d_stage_distortion(bmq3d_solver *s, float *vel_d2, float *scalar_d2, float *max_disp_z)
 {
     NEED(s);
-    float a = 0, b = 0, c = 0;
-    RET_IF(stage_distortion(s, &a, &b, &c));
+    float a = 0, b = 0, c[2] = {0, 0};
+    RET_IF(stage_distortion(s, &a, &b, c));
     if (vel_d2) *vel_d2 = a;
     if (scalar_d2) *scalar_d2 = b;
-    if (max_disp_z) *max_disp_z = c;
-    s->stats.max_disp_z = c;
+    if (max_disp_z) *max_disp_z = s->stats.max_disp_z;
+    return BMQ_OK;
+}
+int bmq3d_stage_distortion2(bmq3d_solver *s, float *vel_d2, float *scalar_d2, float *disp_z_vel, float *disp_z_scalar)
+{
+    NEED(s);
+    float a = 0, b = 0, c[2] = {0, 0};
+    RET_IF(stage_distortion(s, &a, &b, c));
+    if (vel_d2) *vel_d2 = a;
+    if (scalar_d2) *scalar_d2 = b;
+    if (disp_z_vel) *disp_z_vel = c[0];
+    if (disp_z_scalar) *disp_z_scalar = c[1];
     return BMQ_OK;
 }
 int bmq3d_stage_decide(bmq3d_solver *s, int framenum, float dt, float vel_d2, float scalar_d2)
@@ -709,9 +755,8 @@ int bmq3d_advect(bmq3d_solver *s, int framenum, float dt, int with_semilag)
 int bmq3d_accumulate(bmq3d_solver *s, int framenum, float dt)
 {
     NEED(s);
-    float vd2 = 0, sd2 = 0, dz = 0;
-    RET_IF(stage_distortion(s, &vd2, &sd2, &dz));
-    s->stats.max_disp_z = dz;
+    float vd2 = 0, sd2 = 0, dz[2] = {0, 0};
+    RET_IF(stage_distortion(s, &vd2, &sd2, dz));
     decide(s, framenum, dt, vd2, sd2);
     RET_IF(stage_accumulate(s, 0));
     RET_IF(stage_accumulate(s, 1));
@@ -858,9 +903,8 @@ int bmq3d_accumulate_host(bmq3d_solver *s, int framenum, float dt, const float *
         RET_IF(upload_async(s, s->scratch[c], fin[c], ev[5 + 2 * c]));
     }
     for (int c = 3; c < 5; ++c) RET_IF(upload_async(s, s->scratch[c], fin[c], ev[7 + c]));
-    float vd2 = 0, sd2 = 0, dz = 0;
-    RET_IF(stage_distortion(s, &vd2, &sd2, &dz));
-    s->stats.max_disp_z = dz;
+    float vd2 = 0, sd2 = 0, dz[2] = {0, 0};
+    RET_IF(stage_distortion(s, &vd2, &sd2, dz));
     decide(s, framenum, dt, vd2, sd2);
     for (int c = 0; c < 3; ++c) {
         Field &cur = s->f[BMQ_F_U + c], &ext = s->f[BMQ_F_DU_EXT + c], &proj = s->f[BMQ_F_DU_PROJ + c], &stg = s->scratch[c];

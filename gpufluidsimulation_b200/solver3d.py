@@ -253,6 +253,10 @@ class BimocqAdvection3D:
         except Exception:
             pass
 
+    def grow_halo(self, new_halo):
+        """Slab handles: re-allocate every field with a wider halo (device pointers change)."""
+        check(self.lib.bmq3d_grow_halo(self._h, int(new_halo)), "bmq3d_grow_halo")
+
     def set_stream(self, torch_stream):
         check(self.lib.bmq3d_set_stream(self._h, C.c_void_p(torch_stream.cuda_stream if torch_stream else 0)))
 

@@ -13,9 +13,14 @@ scalar max-reductions per step:
 * map-indirected gathers (advect / error / apply / accumulate / forward trace / distortion)
   read at MAP VALUES, whose displacement accumulates since the last re-initialisation
                                        -> halo = ceil(D + CFL_frame) + 3 planes,
-  where D = max |map_z - z| measured by the distortion kernel of the previous step and
-  all-reduced.  If that exceeds the allocated halo the step raises HaloTooNarrow (loudly;
-  nothing is computed from stale data).
+  where D = max |map_z - z| of THAT MAPPER's maps, measured by the distortion kernel of the
+  previous step and all-reduced.  The velocity mapper is re-initialised at least every 10 frames,
+  the scalar mapper every 30 (BimocqSolver.cpp:175-185), so the two sets of fields are exchanged
+  with different widths.  A halo may be wider than the neighbouring slab: the planes then come
+  from the ranks that own them (halo_segments).  If a width exceeds the allocated halo, every
+  rank re-allocates its fields with a wider one (bmq3d_grow_halo; the decision is taken from
+  all-reduced numbers, so all ranks take it in the same step) -- HaloTooNarrow is raised only by
+  rank types that cannot grow.  Nothing is ever computed from stale data.
 
 The step is written once against a small rank/communicator interface, so the same code drives
 (a) real ranks over NCCL, (b) N logical ranks on ONE GPU (LocalComm; used by the GPU tests, where
@@ -30,6 +35,7 @@ import math
 import numpy as np
 
 NARROW = 5          # planes: reach of one DMC sub-step (<= ~3.2 cells) + stencil
+GROW_SLACK = 8      # extra planes allocated when a halo has to grow (so that it grows rarely)
 VEL = ("U", "V", "W")
 CUR = ("U", "V", "W", "RHO", "T")
 INIT = ("U_INIT", "V_INIT", "W_INIT", "RHO_INIT", "T_INIT")
@@ -37,6 +43,8 @@ PREV = ("U_PREV", "V_PREV", "W_PREV", "RHO_PREV", "T_PREV")
 ADV = ("U_ADV", "V_ADV", "W_ADV", "RHO_ADV", "T_ADV")
 ERR = ("U_ERR", "V_ERR", "W_ERR", "RHO_ERR", "T_ERR")
 CHANGE = ("DU_EXT", "DV_EXT", "DW_EXT", "DRHO_EXT", "DT_EXT", "DU_PROJ", "DV_PROJ", "DW_PROJ")
+CHANGE_V = ("DU_EXT", "DV_EXT", "DW_EXT", "DU_PROJ", "DV_PROJ", "DW_PROJ")
+CHANGE_S = ("DRHO_EXT", "DT_EXT")
 MAPS_BWD = tuple(f"{p}BWD_{a}" for p in "VS" for a in "XYZ")
 MAPS_FWD = tuple(f"{p}FWD_{a}" for p in "VS" for a in "XYZ")
 MAPS_BWDP = tuple(f"{p}BWDP_{a}" for p in "VS" for a in "XYZ")
@@ -58,10 +66,18 @@ def slab_bounds(nk: int, world: int, rank: int):
     return k0, k0 + base + (1 if rank < rem else 0)
 
 
+def default_halo(cfl_frame: float = 1.5) -> int:
+    """Halo planes to allocate so that the step does not have to grow them in the common case: the
+    scalar mapper is re-initialised after at most 31 frames (BimocqSolver.cpp:181), a map point
+    moves at most CFL_frame cells per frame; plus this frame's reach and the stencil."""
+    return int(math.ceil(32 * cfl_frame)) + 3
+
+
 def halo_planes(name: str, nk: int, k0: int, k1: int, world: int, rank: int, width: int):
     """Global plane ranges (lower_recv, upper_recv, send_down, send_up) of one field for an
-    exchange of `width` planes; None where there is no neighbour.  The upper halo carries one
-    extra plane (the +1 node of the trilinear stencil)."""
+    exchange of `width` planes with the DIRECT neighbours; None where there is no neighbour.  The
+    upper halo carries one extra plane (the +1 node of the trilinear stencil).  Geometry helper;
+    the exchanges themselves use halo_segments, which also reaches past the direct neighbour."""
     nz = nk + (1 if name in W_TYPE else 0)
     lower_recv = upper_recv = send_down = send_up = None
     if rank > 0:
@@ -73,8 +89,39 @@ def halo_planes(name: str, nk: int, k0: int, k1: int, world: int, rank: int, wid
     return lower_recv, upper_recv, send_down, send_up
 
 
+def owned_range(name: str, nk: int, world: int, rank: int):
+    """Global planes [a, b) of field `name` that rank `rank` owns (w faces: the top face nk belongs
+    to the last rank)."""
+    k0, k1 = slab_bounds(nk, world, rank)
+    return k0, k1 + (1 if name in W_TYPE and rank == world - 1 else 0)
+
+
+def halo_segments(name: str, nk: int, world: int, rank: int, width: int):
+    """What rank `rank` receives for a halo of `width` planes of field `name`:
+    [(source rank, a, b)] with [a, b) global planes owned by the source.  The halo may be wider than
+    the neighbouring slab: segments then come from ranks further away."""
+    nz = nk + (1 if name in W_TYPE else 0)
+    a0, b0 = owned_range(name, nk, world, rank)
+    want = []
+    if rank > 0:
+        want.append((max(0, a0 - width), a0))
+    if rank < world - 1:
+        want.append((b0, min(b0 + width + 1, nz)))
+    out = []
+    for lo, hi in want:
+        for q in range(world):
+            if q == rank:
+                continue
+            qa, qb = owned_range(name, nk, world, q)
+            a, b = max(lo, qa), min(hi, qb)
+            if a < b:
+                out.append((q, a, b))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
-# communicators
+# communicators.  An exchange is a list of GROUPS [(field names, width), ...] moved under one
+# synchronisation point (the two mappers' fields travel together but with their own widths).
 # ----------------------------------------------------------------------------------------------
 class LocalComm:
     """All ranks live in this process (one device): halo exchange = tensor copies."""
@@ -82,20 +129,17 @@ class LocalComm:
     def __init__(self, world):
         self.world = world
 
-    def exchange(self, ranks, names, width):
+    def exchange(self, ranks, groups):
         for r in ranks:
-            for name in names:
-                t, p0 = r.field_with_origin(name)
-                lo, up, _, _ = halo_planes(name, r.nk, r.k0, r.k1, self.world, r.rank, width)
-                if lo is not None:
-                    src, q0 = ranks[r.rank - 1].field_with_origin(name)
-                    t[lo[0] - p0:lo[1] - p0].copy_(src[lo[0] - q0:lo[1] - q0])
-                if up is not None:
-                    src, q0 = ranks[r.rank + 1].field_with_origin(name)
-                    t[up[0] - p0:up[1] - p0].copy_(src[up[0] - q0:up[1] - q0])
+            for names, width in groups:
+                for name in names:
+                    t, p0 = r.field_with_origin(name)
+                    for q, a, b in halo_segments(name, r.nk, self.world, r.rank, width):
+                        src, q0 = ranks[q].field_with_origin(name)
+                        t[a - p0:b - p0].copy_(src[a - q0:b - q0])
 
-    def exchange_async(self, ranks, names, width):
-        self.exchange(ranks, names, width)      # one process, one stream: nothing to overlap
+    def exchange_async(self, ranks, groups):
+        self.exchange(ranks, groups)      # one process, one stream: nothing to overlap
         return None
 
     def wait(self, handle):
@@ -104,36 +148,38 @@ class LocalComm:
     def allreduce_max(self, per_rank_values):
         return [max(v) for v in zip(*per_rank_values)]
 
+    def rebuild(self, ranks, regrow):
+        regrow()
+
 
 class DistComm:
-    """One rank per process: neighbour send/recv batched per exchange, max all-reduce for scalars."""
+    """One rank per process: send/recv batched per exchange, max all-reduce for scalars."""
 
     def __init__(self, world, rank, device):
         import torch.distributed as dist
         self.dist = dist
         self.world, self.rank, self.device = world, rank, device
 
-    def exchange_async(self, ranks, names, width):
+    def exchange_async(self, ranks, groups):
         """Posts the sends/receives of one halo exchange on the communicator's stream and returns
-        the requests; the transfer overlaps whatever is launched before wait()."""
+        the requests; the transfer overlaps whatever is launched before wait().  Every rank walks
+        the same global list of (destination, source, planes), so sends and receives pair up."""
         dist = self.dist
         (r,) = ranks
         ops = []
-        for name in names:
-            t, p0 = r.field_with_origin(name)
-            lo, up, down, upsend = halo_planes(name, r.nk, r.k0, r.k1, self.world, self.rank, width)
-            if down is not None:
-                ops.append(dist.P2POp(dist.isend, t[down[0] - p0:down[1] - p0], self.rank - 1))
-            if upsend is not None:
-                ops.append(dist.P2POp(dist.isend, t[upsend[0] - p0:upsend[1] - p0], self.rank + 1))
-            if lo is not None:
-                ops.append(dist.P2POp(dist.irecv, t[lo[0] - p0:lo[1] - p0], self.rank - 1))
-            if up is not None:
-                ops.append(dist.P2POp(dist.irecv, t[up[0] - p0:up[1] - p0], self.rank + 1))
+        for names, width in groups:
+            for name in names:
+                t, p0 = r.field_with_origin(name)
+                for dst in range(self.world):
+                    for src, a, b in halo_segments(name, r.nk, self.world, dst, width):
+                        if src == self.rank:
+                            ops.append(dist.P2POp(dist.isend, t[a - p0:b - p0], dst))
+                        elif dst == self.rank:
+                            ops.append(dist.P2POp(dist.irecv, t[a - p0:b - p0], src))
         return dist.batch_isend_irecv(ops) if ops else []
 
-    def exchange(self, ranks, names, width):
-        self.wait(self.exchange_async(ranks, names, width))
+    def exchange(self, ranks, groups):
+        self.wait(self.exchange_async(ranks, groups))
 
     def wait(self, handle):
         for req in handle or ():
@@ -146,19 +192,22 @@ class DistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return [float(x) for x in t.tolist()]
 
+    def rebuild(self, ranks, regrow):
+        regrow()
+
 
 class PeerComm(DistComm):
     """Halo exchange by direct peer-to-peer copies over NVLink instead of NCCL send/recv.
 
-    Every rank exports CUDA IPC handles of all its field allocations once; the z-neighbours map
+    Every rank exports CUDA IPC handles of all its field allocations once; every other rank maps
     them.  An exchange is then (1) a stream-ordered barrier -- a one-element NCCL all-reduce, so
     every rank's producer kernel has finished, without blocking any host -- and (2) each rank
-    PULLING its halo planes straight out of the neighbours' owned planes with cudaMemcpyAsync on a
+    PULLING its halo planes straight out of the owners' planes with cudaMemcpyAsync on a
     dedicated copy stream (measured: NCCL send/recv of these 10 MB blocks reaches < 100 GB/s on
     this box, a peer copy ~700 GB/s).  The copy stream is joined to the compute stream by events,
     so an exchange posted with exchange_async overlaps the kernels launched before wait().
 
-    Safety of reading a neighbour's buffer without a second barrier: a source buffer is only
+    Safety of reading another rank's buffer without a second barrier: a source buffer is only
     rewritten by its owner after at least one later exchange (barrier), and a rank's pulls are
     ordered before its own arrival at that barrier (zslab.ZSlabStepper schedule)."""
 
@@ -174,15 +223,22 @@ class PeerComm(DistComm):
         self.lib = slab_rank.solver.lib
         self.copy_stream = torch.cuda.Stream(device=device)
         self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.index_of_ptr = {}
+        self.peer = {}
+        self._connect()
+
+    def _connect(self):
+        """Collective: export this rank's allocations, map everybody else's.  Every rank takes part
+        in every collective below even if a local step failed, and the outcome is agreed on with a
+        MIN all-reduce, so that either all ranks use peer copies or all of them raise
+        PeerUnavailable (the caller then falls back to NCCL send/recv)."""
         from .capi import BimocqLibraryError, check
+        torch, world, rank, slab_rank = self.torch, self.world, self.rank, self.r
         n = len(self.ALLOC_NAMES)
         handles = torch.zeros((n, 64), dtype=torch.uint8)
         self.index_of_ptr = {}
         self.peer = {}
         ok = 1.0
-        # every rank takes part in every collective below even if a local step failed, and the
-        # outcome is agreed on with a MIN all-reduce, so that either all ranks use peer copies or
-        # all of them raise PeerUnavailable (the caller then falls back to NCCL send/recv)
         try:
             for i, name in enumerate(self.ALLOC_NAMES):
                 ptr = slab_rank.solver.field_info(name)[0]
@@ -192,13 +248,13 @@ class PeerComm(DistComm):
                 self.index_of_ptr[ptr] = i
         except BimocqLibraryError:
             ok = 0.0
-        mine = handles.to(device)
+        mine = handles.to(self.device)
         everyone = [torch.zeros_like(mine) for _ in range(world)]
         self.dist.all_gather(everyone, mine)
         gathered = [g.cpu() for g in everyone]
         try:
-            for nb in (rank - 1, rank + 1):
-                if 0 <= nb < world and ok:
+            for nb in range(world):
+                if nb != rank and ok:
                     ptrs = []
                     self.peer[nb] = ptrs
                     for i in range(n):
@@ -208,12 +264,21 @@ class PeerComm(DistComm):
                         ptrs.append(out.value)
         except BimocqLibraryError:
             ok = 0.0
-        agreed = torch.tensor([ok], dtype=torch.float32, device=device)
+        agreed = torch.tensor([ok], dtype=torch.float32, device=self.device)
         self.dist.all_reduce(agreed, op=self.dist.ReduceOp.MIN)
         if float(agreed.item()) < 1.0:
             self.close()
             self.lib.bmq_clear_error()
             raise PeerUnavailable("CUDA IPC peer mapping failed on at least one rank")
+
+    def rebuild(self, ranks, regrow):
+        """bmq3d_grow_halo moves every allocation: finish all pulls, unmap the peers' buffers, barrier
+        (nobody frees a buffer that a peer still has mapped or in use), re-allocate, export and map again."""
+        self.torch.cuda.synchronize()
+        self.close()
+        self.dist.barrier()
+        regrow()
+        self._connect()
 
     @staticmethod
     def _check(status, what):
@@ -224,7 +289,7 @@ class PeerComm(DistComm):
         k0, _ = slab_bounds(self.r.nk, self.world, rank)
         return max(0, k0 - self.r.halo)
 
-    def exchange_async(self, ranks, names, width):
+    def exchange_async(self, ranks, groups):
         torch = self.torch
         (r,) = ranks
         # (1) barrier in stream order: all producers (on every rank) are complete afterwards
@@ -234,20 +299,18 @@ class PeerComm(DistComm):
         ev.record(torch.cuda.current_stream())
         self.copy_stream.wait_event(ev)
         cs = C.c_void_p(self.copy_stream.cuda_stream)
-        for name in names:
-            ptr, p0, npl, nx, ny = r.solver.field_info(name)
-            idx = self.index_of_ptr[ptr]
-            plane = nx * ny
-            lo, up, _, _ = halo_planes(name, r.nk, r.k0, r.k1, self.world, self.rank, width)
-            for rng, nb in ((lo, self.rank - 1), (up, self.rank + 1)):
-                if rng is None:
-                    continue
-                q0 = self._stored_origin(nb)
-                src = self.peer[nb][idx] + 4 * plane * (rng[0] - q0)
-                dst = ptr + 4 * plane * (rng[0] - p0)
-                st = self.lib.bmq_copy_async(C.c_void_p(dst), C.c_void_p(src), 4 * plane * (rng[1] - rng[0]), cs)
-                if st != 0:
-                    self._check(st, "bmq_copy_async")
+        for names, width in groups:
+            for name in names:
+                ptr, p0, npl, nx, ny = r.solver.field_info(name)
+                idx = self.index_of_ptr[ptr]
+                plane = nx * ny
+                for q, a, b in halo_segments(name, r.nk, self.world, self.rank, width):
+                    q0 = self._stored_origin(q)
+                    src = self.peer[q][idx] + 4 * plane * (a - q0)
+                    dst = ptr + 4 * plane * (a - p0)
+                    st = self.lib.bmq_copy_async(C.c_void_p(dst), C.c_void_p(src), 4 * plane * (b - a), cs)
+                    if st != 0:
+                        self._check(st, "bmq_copy_async")
         done = torch.cuda.Event()
         done.record(self.copy_stream)
         return done
@@ -287,6 +350,12 @@ class CudaSlabRank:
             self._views[key] = t
         return t, p0
 
+    def grow_halo(self, new_halo):
+        """Re-allocate every field with a wider halo (owned planes and old halos are kept)."""
+        self._views = {}
+        self.solver.grow_halo(new_halo)
+        self.halo = new_halo
+
     # -- stages (one kernel family each, owned planes only)
     def maxvel(self):
         m = C.c_float()
@@ -316,9 +385,10 @@ class CudaSlabRank:
         self.solver.stage("blend", which)
 
     def distortion(self):
-        a, b, c = C.c_float(), C.c_float(), C.c_float()
-        self.solver.stage("distortion", C.byref(a), C.byref(b), C.byref(c))
-        return a.value, b.value, c.value
+        """(velocity d^2, scalar d^2, velocity-map z displacement, scalar-map z displacement)"""
+        a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        self.solver.stage("distortion2", C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
 
     def decide(self, frame, dt, vd2, sd2):
         self.solver.stage("decide", int(frame), C.c_float(dt), C.c_float(vd2), C.c_float(sd2))
@@ -344,14 +414,16 @@ class ZSlabStepper:
 
     def __init__(self, ranks, comm, blend=1.0):
         self.ranks, self.comm, self.blend = ranks, comm, float(blend)
-        self.disp = 0.0            # max |map_z - z| in cells, from the previous distortion stage
+        # max |map_z - z| in cells per mapper (velocity, scalar): current maps (from the previous
+        # distortion stage) and the maps frozen into chi_prev at the last re-initialisation
+        self.disp = [0.0, 0.0]
+        self.disp_prev = [0.0, 0.0]
         self.halo = ranks[0].halo
         self.nk = ranks[0].nk
         self.h = ranks[0].h
-        self.min_slab = min(slab_bounds(self.nk, comm.world, r)[1] - slab_bounds(self.nk, comm.world, r)[0]
-                            for r in range(comm.world))
         self.stats = {}
         self.reinit_count = [0, 0]
+        self.grow_count = 0
         import os
         self.profile = bool(os.environ.get("BMQ_ZSLAB_PROFILE"))
         self.prof = {}
@@ -364,10 +436,17 @@ class ZSlabStepper:
             self._each = lambda fn: self._timed("stages", lambda: each(fn))
 
     def _width(self, want):
+        """Halo planes for a reach of `want`; grows every rank's halo when the allocation is too
+        narrow.  `want` derives from all-reduced numbers only, so all ranks grow in the same call."""
         w = int(want)
-        if w > self.halo or w + 1 > self.min_slab:
-            raise HaloTooNarrow(f"need {w} halo planes (map displacement {self.disp:.2f} cells), allocated {self.halo}, "
-                                f"smallest slab {self.min_slab}")
+        if w > self.halo:
+            if not all(hasattr(r, "grow_halo") for r in self.ranks):
+                raise HaloTooNarrow(f"need {w} halo planes (map displacement {max(self.disp):.2f} cells), "
+                                    f"allocated {self.halo}")
+            new = w + GROW_SLACK
+            self.comm.rebuild(self.ranks, lambda: [r.grow_halo(new) for r in self.ranks])
+            self.halo = new
+            self.grow_count += 1
         return w
 
     def _each(self, fn):
@@ -397,12 +476,21 @@ class ZSlabStepper:
         (gmax,) = comm.allreduce_max(self._each(lambda r: (r.maxvel(),)))
         cfldt = self._each(lambda r: r.set_cfl(frame, gmax))[0]
         cfl_frame = dt * max(gmax, 1e-4) / self.h
-        wide = self._width(math.ceil(self.disp + cfl_frame) + 3)
+        # widest first, so that a growth happens before anything is in flight
+        need = [math.ceil(self.disp[m] + cfl_frame) + 3 for m in (0, 1)]
+        blend_on = [self.blend != 1.0 and self.reinit_count[m] > 0 for m in (0, 1)]
+        need_b = [math.ceil(self.disp_prev[m] + self.disp[m] + cfl_frame) + 3 if blend_on[m] else 0 for m in (0, 1)]
+        self._width(max(need + need_b + [NARROW]))
+        wv, ws = self._width(need[0]), self._width(need[1])
+        wmax = max(wv, ws)
         narrow = self._width(NARROW)
-        self.stats.update(max_abs_vel=gmax, cfldt=cfldt, halo_used=wide)
-        comm.exchange(ranks, VEL, wide)                       # consumer: DMC (next kernel)
-        comm.exchange(ranks, MAPS_BWD, narrow)
-        h_init = comm.exchange_async(ranks, INIT, wide)       # consumer: advect; overlaps DMC + forward
+        self.stats.update(max_abs_vel=gmax, cfldt=cfldt, halo_used=wmax, halo_vel=wv, halo_scalar=ws,
+                          halo_allocated=self.halo)
+        both = lambda names5: [(names5[0:3], wv), (names5[3:5], ws)]
+        maps = lambda names6, a, b: [(names6[0:3], a), (names6[3:6], b)]
+        comm.exchange(ranks, [(VEL, wmax)])                   # consumers: DMC (next kernel), forward
+        comm.exchange(ranks, [(MAPS_BWD, narrow)])
+        h_init = comm.exchange_async(ranks, both(INIT))       # consumer: advect; overlaps DMC + forward
         # updateBackward (Mapping.cpp:354-368): the reference's float sub-step loop
         T = np.float32(0.0); sub = np.float32(cfldt); dt32 = np.float32(dt)
         n = 0
@@ -414,43 +502,45 @@ class ZSlabStepper:
             T = np.float32(T + sub)
             n += 1
             if T < dt32:
-                comm.exchange(ranks, MAPS_BWD, narrow)        # consumer: the next sub-step
+                comm.exchange(ranks, [(MAPS_BWD, narrow)])    # consumer: the next sub-step
             else:
-                h_bwd = comm.exchange_async(ranks, MAPS_BWD, wide)   # overlaps forward
+                h_bwd = comm.exchange_async(ranks, maps(MAPS_BWD, wv, ws))   # overlaps forward
         self.stats["n_substeps"] = n
         self._each(lambda r: r.forward(dt))                   # psi is read at the own cell only
-        h_fwd = comm.exchange_async(ranks, MAPS_FWD, wide)    # consumer: error; overlaps advect
+        h_fwd = comm.exchange_async(ranks, maps(MAPS_FWD, wv, ws))   # consumer: error; overlaps advect
         comm.wait(h_bwd)
         comm.wait(h_init)
         self._each(lambda r: r.advect(0))
-        h_av = comm.exchange_async(ranks, ADV[0:3], wide)     # overlaps advect(scalars)
+        h_av = comm.exchange_async(ranks, [(ADV[0:3], wv)])   # overlaps advect(scalars)
         self._each(lambda r: r.advect(1))
-        h_as = comm.exchange_async(ranks, ADV[3:5], wide)     # overlaps error(velocity)
+        h_as = comm.exchange_async(ranks, [(ADV[3:5], ws)])   # overlaps error(velocity)
         comm.wait(h_fwd)
         comm.wait(h_av)
         self._each(lambda r: r.error(0))
-        h_ev = comm.exchange_async(ranks, ERR[0:3], wide)     # overlaps error(scalars)
+        h_ev = comm.exchange_async(ranks, [(ERR[0:3], wv)])   # overlaps error(scalars)
         comm.wait(h_as)
         self._each(lambda r: r.error(1))
-        h_es = comm.exchange_async(ranks, ERR[3:5], wide)     # overlaps apply(velocity)
+        h_es = comm.exchange_async(ranks, [(ERR[3:5], ws)])   # overlaps apply(velocity)
         comm.wait(h_ev)
         self._each(lambda r: r.apply(0))
         comm.wait(h_es)
         self._each(lambda r: r.apply(1))
         for which, sl in ((0, slice(0, 3)), (1, slice(3, 5))):
-            if self.blend != 1.0 and self.reinit_count[which] > 0:
-                full = self._width(self.halo)
-                comm.exchange(ranks, PREV[sl], full)
-                comm.exchange(ranks, MAPS_BWDP[which * 3:which * 3 + 3], full)
+            if blend_on[which]:
+                # chi_prev(chi(x)) reaches the displacement frozen at the last reinit on top of the
+                # current one
+                wb = self._width(need_b[which])
+                comm.exchange(ranks, [(PREV[sl], wb), (MAPS_BWDP[which * 3:which * 3 + 3], wb)])
                 self._each(lambda r: r.blend(which))
 
     def accumulate(self, frame, dt):
         comm, ranks = self.comm, self.ranks
         dt = float(np.float32(dt))
-        wide = self.stats.get("halo_used", self._width(3))
-        h_ch = comm.exchange_async(ranks, CHANGE, wide)       # overlaps the distortion kernel
-        vd2, sd2, disp = comm.allreduce_max(self._each(lambda r: r.distortion()))
-        self.disp = disp
+        wv = self.stats.get("halo_vel", 3)
+        ws = self.stats.get("halo_scalar", 3)
+        h_ch = comm.exchange_async(ranks, [(CHANGE_V, wv), (CHANGE_S, ws)])   # overlaps the distortion kernel
+        vd2, sd2, disp_v, disp_s = comm.allreduce_max(self._each(lambda r: r.distortion()))
+        self.disp = [disp_v, disp_s]
         dec = self._each(lambda r: r.decide(frame, dt, vd2, sd2))
         vel_reinit, sca_reinit = dec[0]
         comm.wait(h_ch)
@@ -460,26 +550,33 @@ class ZSlabStepper:
             self._each(lambda r: r.reinit(0, 0))
             self._each(lambda r: r.reinit(0, 1))
             self.reinit_count[0] += 1
+            self.disp_prev[0], self.disp[0] = self.disp[0], 0.0
         if sca_reinit:
             self._each(lambda r: r.reinit(1, 0))
             self.reinit_count[1] += 1
-        if vel_reinit and sca_reinit:
-            self.disp = 0.0
-        self.stats.update(vel_reinit=vel_reinit, scalar_reinit=sca_reinit, max_disp_z=disp,
-                          vel_d2=vd2, scalar_d2=sd2)
+            self.disp_prev[1], self.disp[1] = self.disp[1], 0.0
+        self.stats.update(vel_reinit=vel_reinit, scalar_reinit=sca_reinit, max_disp_z=max(disp_v, disp_s),
+                          disp_z_vel=disp_v, disp_z_scalar=disp_s, vel_d2=vd2, scalar_d2=sd2,
+                          halo_grown=self.grow_count)
 
 
 # ----------------------------------------------------------------------------------------------
 # user-facing wrapper for one process per GPU (bench.py, multi-GPU tests)
 # ----------------------------------------------------------------------------------------------
 class ZSlabAdvection3D:
-    def __init__(self, ni, nj, nk, h, blend_coeff=1.0, rank=0, world=1, halo=24, transport="peer"):
-        """transport: "peer" = direct P2P copies of peer-mapped memory over NVLink (PeerComm; if the
+    def __init__(self, ni, nj, nk, h, blend_coeff=1.0, rank=0, world=1, halo=None, transport="peer",
+                 cfl_frame=1.5):
+        """halo: planes allocated on both sides of the slab; None = default_halo(cfl_frame), the
+        reach of the scalar mapper's 30-frame re-initialisation cap (it grows on demand anyway).
+        transport: "peer" = direct P2P copies of peer-mapped memory over NVLink (PeerComm; if the
         peer mapping cannot be set up on every rank, all ranks fall back to NCCL and say so on
         stderr), "nccl" = NCCL send/recv (DistComm)."""
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
+        if halo is None:
+            halo = default_halo(cfl_frame)
+        halo = min(int(halo), nk)
         self.r = CudaSlabRank(ni, nj, nk, h, blend_coeff, rank, world, halo)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.transport = transport
@@ -496,6 +593,10 @@ class ZSlabAdvection3D:
             self.comm = DistComm(world, rank, dev)
         self.stepper = ZSlabStepper([self.r], self.comm, blend_coeff)
         self.lib = self.r.solver.lib
+
+    @property
+    def halo(self):
+        return self.stepper.halo
 
     def _own_slice(self, name, full):
         """The planes of a whole-grid tensor that this rank stores."""

@@ -244,6 +244,8 @@ typedef struct bmq3d_stats {
     int vel_reinit_count;     /* MapperBase::total_reinit_count                                  */
     int scalar_reinit_count;
     float max_disp_z;         /* max |map_z - z| over both mappers, in cells (halo sizing)       */
+    float max_disp_z_vel;     /* the same per mapper: the velocity mapper is reinitialised at    */
+    float max_disp_z_scalar;  /* least every 10 frames, the scalar mapper every 30               */
 } bmq3d_stats;
 
 /* Creates a solver for an ni x nj x nk grid of cell size h on the current CUDA device.
@@ -316,6 +318,12 @@ int bmq3d_stage_error(bmq3d_solver *s, int which);                    /* e0 = qu
 int bmq3d_stage_apply(bmq3d_solver *s, int which);                    /* f = clamp(f_adv-.5 quad9[e0 o chi]) */
 int bmq3d_stage_blend(bmq3d_solver *s, int which);                    /* two-level blend, if active */
 int bmq3d_stage_distortion(bmq3d_solver *s, float *vel_d2, float *scalar_d2, float *max_disp_z);
+/* same, with the z-displacement (cells) of each mapper's maps: halo widths are sized per mapper */
+int bmq3d_stage_distortion2(bmq3d_solver *s, float *vel_d2, float *scalar_d2, float *disp_z_vel,
+                            float *disp_z_scalar);
+/* Slab handles: re-allocate every field with `new_halo` (> current) halo planes, keeping the stored
+ * planes; device pointers change (re-export IPC handles).  New planes are zero until exchanged. */
+int bmq3d_grow_halo(bmq3d_solver *s, int new_halo);
 int bmq3d_stage_decide(bmq3d_solver *s, int framenum, float dt, float vel_d2, float scalar_d2);
 int bmq3d_stage_accumulate(bmq3d_solver *s, int which);
 int bmq3d_stage_reinit(bmq3d_solver *s, int which, int phase);        /* phase 0: rotate+identity; 1: post-accumulate */

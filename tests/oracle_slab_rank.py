@@ -45,6 +45,16 @@ class OracleSlabRank:
         self.f[name] = o3.padded((p1 - p0, ny, nx))
         self.p0[name] = p0
 
+    def grow_halo(self, new_halo):
+        """Same contract as bmq3d_grow_halo: wider storage, stored planes kept, new planes zero."""
+        old_f, old_p0 = self.f, self.p0
+        self.f, self.p0, self.halo = {}, {}, new_halo
+        for name, a in old_f.items():
+            kind = KIND.get(name, "c")
+            self._alloc(name, kind)
+            off = old_p0[name] - self.p0[name]
+            self.f[name][off:off + a.shape[0]] = a
+
     def field_with_origin(self, name):
         return torch.from_numpy(self.f[name]), self.p0[name]
 
@@ -149,9 +159,10 @@ class OracleSlabRank:
 
     def distortion(self):
         out = []
-        disp = 0.0
+        disps = []
         kb, ke = self.own(0)
         for which in (0, 1):
+            disp = 0.0
             d = o3.padded(self.f["RHO"].shape)
             dv = o3.VirtualArray(d, self.p0["RHO"] * d.shape[1] * d.shape[2])
             bw, fw = self._maps(zslab.MAPS_BWD, which), self._maps(zslab.MAPS_FWD, which)
@@ -163,7 +174,8 @@ class OracleSlabRank:
                 mz = self.f[group[which * 3 + 2]]
                 q0 = self.p0[group[which * 3 + 2]]
                 disp = max(disp, float(np.abs(mz[kb - q0:ke - q0] - zs).max()) / self.h)
-        return out[0], out[1], disp
+            disps.append(disp)
+        return out[0], out[1], disps[0], disps[1]
 
     def decide(self, frame, dt, vd2, sd2):
         dt32 = np.float32(dt)

@@ -16,7 +16,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, halo, frames, dt = 64, 14, 6, 0.02
+    n, halo, frames, dt = 64, 8, 14, 0.02      # the halo has to grow on the way (bmq3d_grow_halo + IPC re-mapping)
     ni, nj, nk = n, n - 8, n + 8
     h = 1.0 / ni
     dev = torch.device("cuda", local)
@@ -73,6 +73,7 @@ def run(transport, rank, world, ni, nj, nk, h, halo, frames, dt, u, v, w, rho, T
                 sys.exit(1)
     if rank == 0:
         print(f"[{transport}] bit-identical to the single-GPU run over {frames} frames (+2 through host buffers)", z.stats(), flush=True)
+    assert z.stepper.grow_count >= 1, "the run was meant to exercise the halo growth"
     z.close(); single.close()
 
 
