@@ -107,6 +107,7 @@ _PROTOS = {
     "bmq_version": (C.c_char_p, []),
     "bmq_kernel_launch_count": (C.c_ulonglong, []),
     "bmq_set_pitch_specialisation": (_I, [_I]),
+    "bmq_set_gather_variant": (_I, [_I]),
     "bmq_ipc_export": (_I, [C.c_void_p, C.c_void_p]),
     "bmq_ipc_open": (_I, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bmq_ipc_close": (_I, [C.c_void_p]),

@@ -107,5 +107,6 @@ const char *bmq_version(void) { return "bimocq_b200 0.1 (sm_100a)"; }
 
 unsigned long long bmq_kernel_launch_count(void) { return bmq::kernel_launch_count(); }
 int bmq_set_pitch_specialisation(int on) { bmq::set_pitch_specialisation(on != 0); return BMQ_OK; }
+int bmq_set_gather_variant(int variant) { bmq::set_gather_variant(variant); return BMQ_OK; }
 
 }  // extern "C"

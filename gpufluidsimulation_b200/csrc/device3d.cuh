@@ -19,6 +19,15 @@ struct Grid3 {
     float h, inv_h;   // cell size; 1/h (exact when h is a power of two)
 };
 
+// FIX != 0: the x and y extents are the compile-time constant FIX, so that row and plane pitches of
+// every gather become immediates of the load instructions instead of 64-bit address arithmetic.
+template <int FIX> __device__ __forceinline__ Grid3 fix_grid(const Grid3 &g)
+{
+    Grid3 r = g;
+    if (FIX) { r.ni = FIX; r.nj = FIX; }
+    return r;
+}
+
 struct Frac {
     int i;
     float f, omf;

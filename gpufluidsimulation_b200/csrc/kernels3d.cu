@@ -59,12 +59,6 @@ static inline dim3 grid3(int fi, int fj, KRange r)
 // ------------------------------------------------------------------ forward map (a4)
 // FIX != 0: the x and y extents are the compile-time constant FIX, so that row and plane pitches of
 // every gather become immediates of the load instructions instead of 64-bit address arithmetic.
-template <int FIX> __device__ __forceinline__ Grid3 fix_grid(const Grid3 &g)
-{
-    Grid3 r = g;
-    if (FIX) { r.ni = FIX; r.nj = FIX; }
-    return r;
-}
 
 // forward_kernel, GPU_kernel.cu:127-144: psi <- trace(psi, +dt) in place, NMAP mappers at once
 // (each mapper's particle is independent; tracing two per thread doubles the loads in flight).
@@ -619,6 +613,13 @@ static inline int fix_of(const Grid3 &g)
     if (!g_pitch_spec.load(std::memory_order_relaxed) || g.ni != g.nj) return 0;
     return (g.ni == 512 || g.ni == 256 || g.ni == 128) ? g.ni : 0;
 }
+int march_fix_of(const Grid3 &g) { return fix_of(g); }
+bool march_is_pow2_h(const Grid3 &g) { return is_pow2_h(g); }
+// Gather-kernel variant: 1 (default) = z-marching columns (march3d.cuh), 0 = one windowed cell per thread.
+// Same arithmetic, bit-identical results; the knob lets tests and benchmarks compare the two.
+static std::atomic<int> g_gather_variant{1};
+void set_gather_variant(int v) { g_gather_variant.store(v); }
+static inline bool use_march() { return g_gather_variant.load(std::memory_order_relaxed) == 1; }
 #define DISPATCH_P2_FIX(g, KERNEL, NM, ...)                                                     \
     do {                                                                                        \
         switch (fix_of(g) * 2 + (is_pow2_h(g) ? 1 : 0)) {                                       \
@@ -753,6 +754,10 @@ cudaError_t launch_advect(cudaStream_t s, const Grid3 &g, KRange r, Stag st, boo
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{chi[0], chi[1], chi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0) && use_march()) {
+        count_launch();
+        return launch_advect_march(s, g, r, st, nf, out, init, chi);
+    }
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1) DISPATCH_STAG_P2(g, st, k_advect_win, 1, g, r.kbeg, r.kend, rw<1>(out), ro<1>(init), m);
         else k_dispatch_centred2_advect(s, g, r, gr, bl, out, init, m);
@@ -776,6 +781,10 @@ cudaError_t launch_error(cudaStream_t s, const Grid3 &g, KRange r, Stag st, bool
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{psi[0], psi[1], psi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0) && use_march()) {
+        count_launch();
+        return launch_error_march(s, g, r, st, nf, e0, src, init, psi);
+    }
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1) DISPATCH_STAG_P2(g, st, k_error_win, 1, g, r.kbeg, r.kend, rw<1>(e0), ro<1>(src), ro<1>(init), m);
         else DISPATCH_STAG_P2(g, (Stag{0, 0, 0}), k_error_win, 2, g, r.kbeg, r.kend, rw<2>(e0), ro<2>(src), ro<2>(init), m);
@@ -799,6 +808,10 @@ cudaError_t launch_cumulate(cudaStream_t s, const Grid3 &g, KRange r, Stag st, b
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{map[0], map[1], map[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0) && use_march() && ((nf == 1 && nch <= 2) || (nf == 2 && nch == 1))) {
+        count_launch();
+        return launch_cumulate_march(s, g, r, st, nf, nch, target, change, coeff, map);
+    }
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1 && nch == 1) {
             Coeffs<1> c; c.c[0] = coeff[0];
@@ -836,6 +849,10 @@ cudaError_t launch_apply_clamp(cudaStream_t s, const Grid3 &g, KRange r, Stag st
     if (r.kend <= r.kbeg) return cudaSuccess;
     Map3 m{chi[0], chi[1], chi[2]};
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
+    if (!is_point && (nf == 1 || stag_id(st) == 0) && use_march()) {
+        count_launch();
+        return launch_apply_march(s, g, r, st, nf, out, fadv, e0, chi);
+    }
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {
         if (nf == 1) DISPATCH_STAG_P2(g, st, k_apply_clamp_win, 1, g, r.kbeg, r.kend, rw<1>(out), ro<1>(fadv), ro<1>(e0), m);
         else DISPATCH_STAG_P2(g, (Stag{0, 0, 0}), k_apply_clamp_win, 2, g, r.kbeg, r.kend, rw<2>(out), ro<2>(fadv), ro<2>(e0), m);

@@ -28,6 +28,18 @@ namespace bmq {
 Grid3 make_grid(int ni, int nj, int nk, float h);
 unsigned long long kernel_launch_count();
 void set_pitch_specialisation(bool on);   // testing knob, see bmq_set_pitch_specialisation
+void set_gather_variant(int v);           // testing knob, see bmq_set_gather_variant
+// z-marching gather kernels (march_*.cu); same contracts as launch_advect / _error / _cumulate / _apply_clamp
+// with is_point == false
+cudaError_t launch_advect_march(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, float *const *out,
+                                const float *const *init, const float *const chi[3]);
+cudaError_t launch_error_march(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, float *const *e0,
+                               const float *const *src, const float *const *init, const float *const psi[3]);
+cudaError_t launch_cumulate_march(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, int nch,
+                                  float *const *target, const float *const *change, const float *coeff,
+                                  const float *const map[3]);
+cudaError_t launch_apply_march(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, float *const *out,
+                               const float *const *fadv, const float *const *e0, const float *const chi[3]);
 
 cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float *u, const float *v,
                            const float *w, int nmap, float *const maps[][3], float cfldt, float dt);

@@ -1,0 +1,516 @@
+// z-marching gather kernels: advect / time-0 error / accumulate / apply-and-clamp.
+//
+// The windowed kernels of kernels3d.cu load, for every output cell, the 3x3x3 (2 along a staggered axis)
+// window of map nodes around it: 81 loads per cell and map, of which 54 are the two z-planes the cell
+// below it has just loaded.  Here a thread owns a COLUMN of cells (i, j, k0..k1): it keeps the x- and
+// y-interpolated values of the last two map planes in registers and loads one new plane per cell
+// (27 loads instead of 81; 12 instead of 38 packed lerps per map component).
+//
+// What bounds these kernels on B200 is neither HBM nor the load count but the FP32 pipe: FFMA / FMUL /
+// FADD / IMAD share one pipe that takes a warp instruction every second cycle per scheduler
+// (B300_MICROARCH.md "Pipe rates"), and a trilinear field sample is ~26 such instructions when written
+// naively.  The gather core below therefore
+//   * works in GRID units when h is a power of two: the scaling by 1/h is folded into the (constant)
+//     z-weights of the map interpolation, which is exact (power-of-two scaling commutes with rounding);
+//   * evaluates the eight corner samples as four PAIRS (x plus, x minus) in packed fp32 (FMUL2 / FFMA2):
+//     the two lanes are the two samples, each lane the scalar operation of the reference nest
+//     x -> y -> z, so every sample is bit-identical to an independent trilerp;
+//   * accumulates the quadrature sum in the reference's order ii = 0..7 (GPU_kernel.cu:350-357).
+// Results are bit-identical to the windowed kernels and, through them, to the reference
+// (GPU_kernel.cu:312-499); tests/test_march_gpu.py compares the two variants.
+//
+// The apply kernel's 27-neighbour extrema clamp (clampExtrema_kernel, GPU_kernel.cu:146-167) marches the
+// same way: min/max of the 3x3 neighbourhood per plane are carried, 9 loads per cell instead of 27.
+#pragma once
+#include <type_traits>
+
+#include "launch3d.h"
+#include "device3d.cuh"
+
+namespace bmq {
+
+enum { GM_ADVECT = 0, GM_ERROR = 1, GM_CUMULATE = 2, GM_APPLY = 3 };
+
+#ifndef BMQ_MARCH_BY
+#define BMQ_MARCH_BY 4          // CTA = 32 x BMQ_MARCH_BY columns
+#endif
+#ifndef BMQ_MARCH_MINBLOCKS
+#define BMQ_MARCH_MINBLOCKS 6   // x 128 threads: 24 warps per SM at <= 80 registers (sweep: profiles/r2_march_variants.md)
+#endif
+#ifndef BMQ_MARCH_UNROLL
+#define BMQ_MARCH_UNROLL 0      // 1: k loop unrolled by the ring period (no register moves, but 3-6x the code: slower); 0: one cell per iteration
+#endif
+#ifndef BMQ_MARCH_PREFETCH
+#define BMQ_MARCH_PREFETCH 1    // 1 / 2: prefetch the next cell's new map plane and field plane into L1 / L2
+#endif
+
+__device__ __forceinline__ void prefetch_line(const float *p)
+{
+#if BMQ_MARCH_PREFETCH == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif BMQ_MARCH_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+template <int NF, int NS> struct MarchArgs {
+    float *out[NF];          // advect: f_adv | error: e0 | cumulate: target (read-modify-write) | apply: f
+    const float *src[NS];    // gathered through the map: init | f_adv | change sets [set][field] | e0
+    const float *aux[NF];    // error: init | apply: f_adv | otherwise unused
+    float coeff[NS / NF];    // cumulate: one coefficient per change set
+};
+
+// x- and y-interpolated values of ONE z-node plane of ONE map component: the part of window_samples
+// (device3d.cuh) that does not depend on z.  yp / ym: y plus / minus point, each a pair over the x sign
+// (.x = plus, .y = minus); c: centre line (power-of-two h only).
+struct PlaneXY {
+    float2 yp, ym;
+    float c;
+};
+
+template <bool P2, int STAG>
+__device__ __forceinline__ PlaneXY plane_xy(const float *__restrict__ p, int sy, const AxisW<P2, STAG == 1> &ax,
+                                            const AxisW<P2, STAG == 2> &ay)
+{
+    constexpr int NX = STAG == 1 ? 2 : 3, NY = STAG == 2 ? 2 : 3;
+    const float2 fx = make_float2(ax.fp, ax.fm), ox = make_float2(ax.op, ax.om);
+    const float2 fym = make_float2(ay.fm, ay.fm), oym = make_float2(ay.om, ay.om);
+    const float2 fyp = make_float2(ay.fp, ay.fp), oyp = make_float2(ay.op, ay.op);
+    float2 X[NY];
+    float xc[NY];
+#pragma unroll
+    for (int y = 0; y < NY; ++y) {
+        const float *r = p + y * sy;
+        const float n0 = __ldg(r), n1 = __ldg(r + 1);
+        const float n2 = NX == 3 ? __ldg(r + 2) : 0.f;
+        X[y] = NX == 3 ? lerp32x2(make_float2(n1, n0), make_float2(n2, n1), fx, ox)
+                       : lerp32x2(make_float2(n0, n0), make_float2(n1, n1), fx, ox);
+        if (P2) xc[y] = NX == 3 ? n1 : lerp32(n0, n1, 0.5f, 0.5f);
+    }
+    PlaneXY o;
+    o.ym = lerp32x2(X[0], X[1], fym, oym);
+    o.yp = NY == 3 ? lerp32x2(X[1], X[2], fyp, oyp) : lerp32x2(X[0], X[1], fyp, oyp);
+    o.c = 0.f;
+    if (P2) o.c = NY == 3 ? xc[1] : lerp32(xc[0], xc[1], 0.5f, 0.5f);
+    return o;
+}
+
+// The z part of window_samples.  pos[ii], ii = 2*(y minus) + (z minus), is the PAIR (x plus, x minus) of
+// corner samples ii and ii + 4 of the reference's order (x sign bit 2, y sign bit 1, z sign bit 0; 0 = plus).
+// `scale` multiplies the z weights: 1 (world units) or 1/h, a power of two (grid units; exact).
+template <bool P2, int STAG>
+__device__ __forceinline__ void z_combine(const PlaneXY &Pa, const PlaneXY &Pb, const PlaneXY &Pc, const AxisW<P2, STAG == 3> &az,
+                                          float scale, float2 (&pos)[4], float &centre)
+{
+    constexpr int NZ = STAG == 3 ? 2 : 3;
+    const float fm = P2 ? az.fm * scale : az.fm, om = P2 ? az.om * scale : az.om;
+    const float fp = P2 ? az.fp * scale : az.fp, op = P2 ? az.op * scale : az.op;
+    const float2 fzm = make_float2(fm, fm), ozm = make_float2(om, om);
+    const float2 fzp = make_float2(fp, fp), ozp = make_float2(op, op);
+#pragma unroll
+    for (int sy_ = 0; sy_ < 2; ++sy_) {
+        const float2 y0 = sy_ ? Pa.ym : Pa.yp, y1 = sy_ ? Pb.ym : Pb.yp, y2 = sy_ ? Pc.ym : Pc.yp;
+        pos[sy_ * 2 + 1] = lerp32x2(y0, y1, fzm, ozm);                                                   // z minus
+        pos[sy_ * 2 + 0] = NZ == 3 ? lerp32x2(y1, y2, fzp, ozp) : lerp32x2(y0, y1, fzp, ozp);            // z plus
+    }
+    if (P2) centre = NZ == 3 ? Pb.c * scale : lerp32(Pa.c, Pb.c, 0.5f * scale, 0.5f * scale);
+}
+
+// ---- the gather core -------------------------------------------------------------------------------------
+// Positions reach it clamped: in cells when GRID (power-of-two h), as world positions otherwise.  Returns
+// (position - field origin) / h, the reference's `pos / h` of sample_buffer (GPU_kernel.cu:46-51).
+template <bool GRID>
+__device__ __forceinline__ float to_cells(float p, float off_world, float off_grid, float h)
+{
+    // GRID: p is already in cells; the staggering offset (+1/2) is the only arithmetic left
+    if (GRID) return off_grid != 0.f ? p + off_grid : p;
+    return __fdiv_rn(off_world != 0.f ? p - off_world : p, h);
+}
+
+struct Split2 {
+    float2 f, omf;
+    int i0, i1;
+};
+// (cell, fraction, 1 - fraction) of two coordinates at once: q - floor(q) and 1 - f as exact FFMA2s with -1
+__device__ __forceinline__ Split2 split2(float2 q)
+{
+    const float2 fl = make_float2(floorf(q.x), floorf(q.y));
+    const float2 m1 = make_float2(-1.0f, -1.0f), one = make_float2(1.0f, 1.0f);
+    Split2 s;
+    s.i0 = (int)fl.x;
+    s.i1 = (int)fl.y;
+#if defined(BMQ_NO_PACKED_FP32) || defined(BMQ_SPLIT2_SCALAR)
+    s.f = make_float2(q.x - fl.x, q.y - fl.y);
+    s.omf = make_float2(1.0f - s.f.x, 1.0f - s.f.y);
+#else
+    s.f = __ffma2_rn(fl, m1, q);         // q - floor(q): exact
+    s.omf = __ffma2_rn(s.f, m1, one);    // 1 - f: the same single rounding as 1.0f - f
+#endif
+    return s;
+}
+
+// two trilinear samples (the two lanes) of NS co-located fields; lane arithmetic = tri8 (device3d.cuh)
+template <int NS>
+__device__ __forceinline__ void gather_pair(const float *const (&src)[NS], int sy, int sz, const Split2 &x, const Split2 &y,
+                                            const Split2 &z, float (&lane0)[NS], float (&lane1)[NS])
+{
+    const int o0 = x.i0 + sy * y.i0 + sz * z.i0, o1 = x.i1 + sy * y.i1 + sz * z.i1;
+#pragma unroll
+    for (int f = 0; f < NS; ++f) {
+        const float *p0 = src[f] + o0, *p1 = src[f] + o1;
+        const float2 n000 = make_float2(__ldg(p0), __ldg(p1)), n001 = make_float2(__ldg(p0 + 1), __ldg(p1 + 1));
+        const float2 n010 = make_float2(__ldg(p0 + sy), __ldg(p1 + sy)), n011 = make_float2(__ldg(p0 + sy + 1), __ldg(p1 + sy + 1));
+        const float2 n100 = make_float2(__ldg(p0 + sz), __ldg(p1 + sz)), n101 = make_float2(__ldg(p0 + sz + 1), __ldg(p1 + sz + 1));
+        const float2 n110 = make_float2(__ldg(p0 + sz + sy), __ldg(p1 + sz + sy));
+        const float2 n111 = make_float2(__ldg(p0 + sz + sy + 1), __ldg(p1 + sz + sy + 1));
+        const float2 a00 = lerp32x2(n000, n001, x.f, x.omf), a01 = lerp32x2(n010, n011, x.f, x.omf);
+        const float2 a10 = lerp32x2(n100, n101, x.f, x.omf), a11 = lerp32x2(n110, n111, x.f, x.omf);
+        const float2 b0 = lerp32x2(a00, a01, y.f, y.omf), b1 = lerp32x2(a10, a11, y.f, y.omf);
+        const float2 c = lerp32x2(b0, b1, z.f, z.omf);
+        lane0[f] = c.x;
+        lane1[f] = c.y;
+    }
+}
+
+// one trilinear sample of NS co-located fields from cell coordinates; returns the offset of its base node
+template <int NS>
+__device__ __forceinline__ int gather_one(const float *const (&src)[NS], int sy, int sz, float qx, float qy, float qz,
+                                          float (&out)[NS], int &zi)
+{
+    Frac x, y, z;
+    float fl;
+    fl = floorf(qx); x.i = (int)fl; x.f = qx - fl; x.omf = 1.0f - x.f;
+    fl = floorf(qy); y.i = (int)fl; y.f = qy - fl; y.omf = 1.0f - y.f;
+    fl = floorf(qz); z.i = (int)fl; z.f = qz - fl; z.omf = 1.0f - z.f;
+    const int o = x.i + sy * y.i + sz * z.i;
+#pragma unroll
+    for (int f = 0; f < NS; ++f) out[f] = tri8(src[f] + o, sy, sz, x, y, z);
+    zi = z.i;
+    return o;
+}
+
+// min / max of the 3x3 (x, y) neighbourhood of one plane, and the centre value
+struct Plane9 {
+    float mn, mx, c;
+};
+__device__ __forceinline__ Plane9 plane9(const float *__restrict__ p, int sy)
+{
+    Plane9 o;
+    o.c = __ldg(p);
+    o.mn = o.mx = o.c;
+#pragma unroll
+    for (int jj = -1; jj <= 1; ++jj)
+#pragma unroll
+        for (int ii = -1; ii <= 1; ++ii) {
+            if (ii == 0 && jj == 0) continue;
+            const float v = __ldg(p + ii + jj * sy);
+            o.mx = fmaxf(o.mx, v);
+            o.mn = fminf(o.mn, v);
+        }
+    return o;
+}
+
+template <int MODE, bool P2, int STAG, int NF, int NCH, int FIX>
+__global__ void __launch_bounds__(32 * BMQ_MARCH_BY, BMQ_MARCH_MINBLOCKS)
+k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map3 m)
+{
+    const Grid3 g = fix_grid<FIX>(g_);
+    constexpr int DX = STAG == 1, DY = STAG == 2, DZ = STAG == 3, NZ = STAG == 3 ? 2 : 3, NS = NF * NCH;
+    constexpr int GL = MODE == GM_ADVECT ? 2 : 1;     // interior guard GL + D < idx < f - GL - 1 (reference :341/:405/:467)
+    const int fi = g.ni + DX, fj = g.nj + DY, fk = g.nk + DZ;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    const int j = blockIdx.y * BMQ_MARCH_BY + threadIdx.y;
+    if (i >= fi || j >= fj) return;
+    const int kc0 = kbeg + blockIdx.z * kchunk;
+    const int kc1 = min(kc0 + kchunk, kend);
+    const bool gij = GL + DX < i && i < fi - GL - 1 && GL + DY < j && j < fj - GL - 1;
+    const int ka = max(kc0, GL + DZ + 1), kb = min(kc1, fk - GL - 1);   // cells [ka, kb) of this column gather
+
+    const float h = g.h;
+    // field origin: -h/2 on the staggered axis (GPU_kernel.cu:212,259,332), exactly 0 elsewhere
+    const float ox = DX ? -0.5f * h : 0.f, oy = DY ? -0.5f * h : 0.f, oz = DZ ? -0.5f * h : 0.f;
+    // explicit roundings: a plain h * i could be contracted into the subtractions of AxisW::init (general h) and
+    // change the map fractions by an ulp
+    const float cx = DX ? fmaf(h, (float)i, ox) : __fmul_rn(h, (float)i), cy = DY ? fmaf(h, (float)j, oy) : __fmul_rn(h, (float)j);
+    // clamp band of the mapped positions: [h, (n-1)h] (advect, :356) or [0, n h] (:419, :479); in cells when P2
+    const float ps = P2 ? g.inv_h : 1.0f;
+    const float lo = (MODE == GM_ADVECT ? h : 0.f) * ps;
+    const float hix = (MODE == GM_ADVECT ? h * (float)g.ni - h : h * (float)g.ni) * ps;
+    const float hiy = (MODE == GM_ADVECT ? h * (float)g.nj - h : h * (float)g.nj) * ps;
+    const float hiz = (MODE == GM_ADVECT ? h * (float)g.nk - h : h * (float)g.nk) * ps;
+    const int col = i + fi * j, fplane = fi * fj;
+
+    if (MODE != GM_APPLY) {
+        if (!gij || ka >= kb) return;
+    } else if (!(i > 0 && i < fi - 1 && j > 0 && j < fj - 1)) {
+        // rim columns of the apply kernel: f = f_adv (the reference leaves f_adv untouched there)
+        for (int k = kc0; k < kc1; ++k)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) a.out[f][col + fplane * k] = __ldg(a.aux[f] + col + fplane * k);
+        return;
+    }
+
+    AxisW<P2, STAG == 1> ax;
+    AxisW<P2, STAG == 2> ay;
+    AxisW<P2, STAG == 3> az;
+    ax.init(cx, h, g.inv_h);
+    ay.init(cy, h, g.inv_h);
+    az.init(0.f, h, g.inv_h);     // power-of-two h: constants; otherwise re-initialised per cell
+    const int sy = g.ni, sz = g.ni * g.nj;
+    const int mbase = (i - 1) + sy * (j - 1);
+    PlaneXY Px[3], Py[3], Pz[3];  // ring of carried map planes: z node n of the cell run by body<R> is slot (R + n) % NZ
+    Plane9 M[NF][3];              // apply: ring of 3x3 extrema of f_adv planes k-1, k, k+1
+    const bool gathers = gij && ka < kb;
+    const int kfirst = MODE == GM_APPLY ? kc0 : ka, klast = MODE == GM_APPLY ? kc1 : kb;
+
+    // One cell.  R = (k - kfirst) % PERIOD selects, at compile time, which ring slots hold the window planes,
+    // so that the carried planes never move between registers.
+#if BMQ_MARCH_PREFETCH == 3
+    // experiment: prefetch by REAL loads whose values are consumed one cell later (proves / disproves that the
+    // L1-miss latency of the new planes is what the cells wait for)
+    float pf_v[16];
+    int pf_sink = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) pf_v[q] = 0.f;
+    const int pf_dx = threadIdx.x == 0 ? 0 : 2;
+#endif
+    auto body = [&](auto Rtag, int k) {
+        constexpr int R = decltype(Rtag)::value;
+#if BMQ_MARCH_PREFETCH == 3
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pf_sink |= __float_as_int(pf_v[q]);
+#endif
+        constexpr int S0 = R % NZ, S1 = (R + 1) % NZ, S2 = (R + 2) % NZ;     // slots of z nodes 0, 1, 2
+        constexpr int SN = NZ == 3 ? S2 : S1;                                // slot the new plane goes to
+        const int idx = col + fplane * k;
+        const bool gk = MODE != GM_APPLY || (gathers && k >= ka && k < kb);
+        float sum[NS], val[NS];
+#pragma unroll
+        for (int f = 0; f < NS; ++f) sum[f] = val[f] = 0.f;
+        if (gk) {
+            const int onew = mbase + sz * (NZ == 3 ? k + 1 : k);
+            Px[SN] = plane_xy<P2, STAG>(m.x + onew, sy, ax, ay);
+            Py[SN] = plane_xy<P2, STAG>(m.y + onew, sy, ax, ay);
+            Pz[SN] = plane_xy<P2, STAG>(m.z + onew, sy, ax, ay);
+            if (BMQ_MARCH_PREFETCH && k + 1 < kb) {
+                // the plane the NEXT cell of this column will load: rows j-1..j+1 (lanes cover i-1..i+30, +1 the rest)
+#pragma unroll
+                for (int y = 0; y < (STAG == 2 ? 2 : 3); ++y) {
+#if BMQ_MARCH_PREFETCH == 3
+                    pf_v[3 * y + 0] = __ldg(m.x + onew + sz + y * sy + pf_dx);
+                    pf_v[3 * y + 1] = __ldg(m.y + onew + sz + y * sy + pf_dx);
+                    pf_v[3 * y + 2] = __ldg(m.z + onew + sz + y * sy + pf_dx);
+#else
+                    prefetch_line(m.x + onew + sz + y * sy + 1);
+                    prefetch_line(m.y + onew + sz + y * sy + 1);
+                    prefetch_line(m.z + onew + sz + y * sy + 1);
+#endif
+                }
+            }
+            const float cz = DZ ? fmaf(h, (float)k, oz) : __fmul_rn(h, (float)k);
+            if (!P2) az.init(cz, h, g.inv_h);
+            float2 px[4], py[4], pz[4];
+            float ccx = 0.f, ccy = 0.f, ccz = 0.f;
+            z_combine<P2, STAG>(Px[S0], Px[S1], Px[S2], az, ps, px, ccx);
+            z_combine<P2, STAG>(Py[S0], Py[S1], Py[S2], az, ps, py, ccy);
+            z_combine<P2, STAG>(Pz[S0], Pz[S1], Pz[S2], az, ps, pz, ccz);
+            if (!P2) {
+                const float3 c = sample_map<false>(m, g, cx, cy, cz);
+                ccx = c.x; ccy = c.y; ccz = c.z;
+            }
+            float wgt[NS];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    wgt[c * NF + f] = MODE == GM_CUMULATE ? 0.125f * a.coeff[c] : MODE == GM_APPLY ? 0.125f * -0.5f : 0.125f;
+            // corner samples ii and ii + 4 as one packed pair; the x-minus halves wait for their turn in the sum
+            float late[4][NS];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                float2 qx, qy, qz;
+                qx.x = to_cells<P2>(clampf(px[ii].x, lo, hix), ox, DX * 0.5f, h);
+                qx.y = to_cells<P2>(clampf(px[ii].y, lo, hix), ox, DX * 0.5f, h);
+                qy.x = to_cells<P2>(clampf(py[ii].x, lo, hiy), oy, DY * 0.5f, h);
+                qy.y = to_cells<P2>(clampf(py[ii].y, lo, hiy), oy, DY * 0.5f, h);
+                qz.x = to_cells<P2>(clampf(pz[ii].x, lo, hiz), oz, DZ * 0.5f, h);
+                qz.y = to_cells<P2>(clampf(pz[ii].y, lo, hiz), oz, DZ * 0.5f, h);
+                const Split2 spx = split2(qx), spy = split2(qy), spz = split2(qz);
+                float s0[NS];
+                gather_pair<NS>(a.src, fi, fplane, spx, spy, spz, s0, late[ii]);
+#pragma unroll
+                for (int f = 0; f < NS; ++f) sum[f] = fmaf(wgt[f], s0[f], sum[f]);
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                for (int f = 0; f < NS; ++f) sum[f] = fmaf(wgt[f], late[ii][f], sum[f]);
+            const float qcx = to_cells<P2>(clampf(ccx, lo, hix), ox, DX * 0.5f, h);
+            const float qcy = to_cells<P2>(clampf(ccy, lo, hiy), oy, DY * 0.5f, h);
+            const float qcz = to_cells<P2>(clampf(ccz, lo, hiz), oz, DZ * 0.5f, h);
+            int zi;
+            const int oc = gather_one<NS>(a.src, fi, fplane, qcx, qcy, qcz, val, zi);
+            if (BMQ_MARCH_PREFETCH && k + 1 < kb && zi + 2 < fk) {
+                // the field plane the next cell's samples will newly touch: two planes above the centre sample's cell
+#pragma unroll
+                for (int f = 0; f < NS; ++f) {
+#if BMQ_MARCH_PREFETCH == 3
+                    pf_v[9 + 2 * f] = __ldg(a.src[f] + oc + 2 * fplane);
+                    pf_v[10 + 2 * f] = __ldg(a.src[f] + oc + 2 * fplane + fi);
+#else
+                    prefetch_line(a.src[f] + oc + 2 * fplane);
+                    prefetch_line(a.src[f] + oc + 2 * fplane + fi);
+#endif
+                }
+            }
+        }
+        if (MODE == GM_ADVECT) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) a.out[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]);
+        } else if (MODE == GM_ERROR) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) a.out[f][idx] = fmaf(0.5f, sum[f], 0.5f * val[f]) - __ldg(a.aux[f] + idx);
+        } else if (MODE == GM_CUMULATE) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float t = a.out[f][idx];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float v = a.coeff[c] * val[c * NF + f];
+                    t += fmaf(0.5f, sum[c * NF + f], 0.5f * v);
+                }
+                a.out[f][idx] = t;
+            }
+        } else {
+            // extrema ring: planes k-1, k, k+1 sit in slots R % 3, (R + 1) % 3, (R + 2) % 3
+            constexpr int Q0 = R % 3, Q1 = (R + 1) % 3, Q2 = (R + 2) % 3;
+            const bool clamps = k > 0 && k < fk - 1;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                M[f][Q2] = k + 1 < fk ? plane9(a.aux[f] + idx + fplane, fi) : M[f][Q1];
+                float r = M[f][Q1].c;
+                if (gk) r += fmaf(0.5f, sum[f], 0.5f * (-0.5f * val[f]));
+                if (clamps) {
+                    const float mx = fmaxf(fmaxf(M[f][Q0].mx, M[f][Q1].mx), M[f][Q2].mx);
+                    const float mn = fminf(fminf(M[f][Q0].mn, M[f][Q1].mn), M[f][Q2].mn);
+                    r = fminf(fmaxf(mn, r), mx);
+                }
+                a.out[f][idx] = r;
+            }
+        }
+    };
+
+    // unrolled by the ring period so that slot indices are compile-time constants (no register moves):
+    // NZ for the gather-only kernels; the apply kernel also rotates a 3-slot extrema ring -> 6
+    constexpr int PERIOD = !BMQ_MARCH_UNROLL ? 1 : MODE == GM_APPLY ? 6 : NZ;
+    // carried planes at loop entry: the window of the first gathering cell minus its newest plane
+    if (gathers) {
+        const int o0 = mbase + sz * (ka - 1);
+        const int r0 = (ka - kfirst) % PERIOD;       // cell ka is run by body<r0>: its z node n sits in slot (r0 + n) % NZ
+#pragma unroll
+        for (int n = 0; n < NZ - 1; ++n) {
+            const PlaneXY qx = plane_xy<P2, STAG>(m.x + o0 + n * sz, sy, ax, ay);
+            const PlaneXY qy = plane_xy<P2, STAG>(m.y + o0 + n * sz, sy, ax, ay);
+            const PlaneXY qz = plane_xy<P2, STAG>(m.z + o0 + n * sz, sy, ax, ay);
+#pragma unroll
+            for (int s = 0; s < NZ; ++s)
+                if ((r0 + n) % NZ == s) { Px[s] = qx; Py[s] = qy; Pz[s] = qz; }
+        }
+    }
+    if (MODE == GM_APPLY) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            M[f][1] = plane9(a.aux[f] + col + fplane * kc0, fi);       // plane k = kc0: slot Q1 of body<0>
+            M[f][0] = kc0 > 0 ? plane9(a.aux[f] + col + fplane * (kc0 - 1), fi) : M[f][1];
+        }
+    }
+    int k = kfirst;
+    if (!BMQ_MARCH_UNROLL) {
+#pragma unroll 1
+        for (; k < klast; ++k) {
+            body(std::integral_constant<int, 0>{}, k);
+            if (MODE != GM_APPLY || (gathers && k >= ka && k < kb)) {
+                Px[0] = Px[1]; Py[0] = Py[1]; Pz[0] = Pz[1];
+                if (NZ == 3) { Px[1] = Px[2]; Py[1] = Py[2]; Pz[1] = Pz[2]; }
+            }
+            if (MODE == GM_APPLY) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) { M[f][0] = M[f][1]; M[f][1] = M[f][2]; }
+            }
+        }
+#if BMQ_MARCH_PREFETCH == 3
+        if (pf_sink == 0x7fc12345) a.out[0][0] = 0.f;
+#endif
+        return;
+    }
+#pragma unroll 1
+    for (; k + PERIOD <= klast; k += PERIOD) {
+        body(std::integral_constant<int, 0>{}, k);
+        body(std::integral_constant<int, 1>{}, k + 1);
+        if (PERIOD > 2) body(std::integral_constant<int, 2>{}, k + 2);
+        if (PERIOD > 3) {
+            body(std::integral_constant<int, 3>{}, k + 3);
+            body(std::integral_constant<int, 4>{}, k + 4);
+            body(std::integral_constant<int, 5>{}, k + 5);
+        }
+    }
+    if (k < klast) body(std::integral_constant<int, 0>{}, k);
+    if (k + 1 < klast) body(std::integral_constant<int, 1>{}, k + 1);
+    if (PERIOD > 3) {
+        if (k + 2 < klast) body(std::integral_constant<int, 2>{}, k + 2);
+        if (k + 3 < klast) body(std::integral_constant<int, 3>{}, k + 3);
+        if (k + 4 < klast) body(std::integral_constant<int, 4>{}, k + 4);
+    }
+}
+
+// ---- host side: grid shape and dispatch over (power-of-two h, staggering, pitch specialisation)
+int march_fix_of(const Grid3 &g);         // kernels3d.cu: 0 or the compile-time plane extent
+bool march_is_pow2_h(const Grid3 &g);
+
+static inline int march_chunk(int fi, int fj, int nplanes)
+{
+    // planes per CTA: long columns amortise the two-plane prologue, but the grid must still fill the
+    // machine (148 SMs x BMQ_MARCH_MINBLOCKS CTAs) a few times over
+    const long long cols = (long long)((fi + 31) / 32) * ((fj + BMQ_MARCH_BY - 1) / BMQ_MARCH_BY);
+    int kc = 32;
+    while (kc > 8 && cols * ((nplanes + kc - 1) / kc) < 148ll * BMQ_MARCH_MINBLOCKS * 4) kc /= 2;
+    return kc;
+}
+
+#define BMQ_MARCH_CASE(MODE, P2V, STAGV, NFV, NCHV, FIXV)                                                     \
+    k_march<MODE, P2V, STAGV, NFV, NCHV, FIXV><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, kc, a, m)
+#define BMQ_MARCH_FIX(MODE, P2V, STAGV, NFV, NCHV)                                                            \
+    switch (fix) {                                                                                            \
+    case 512: BMQ_MARCH_CASE(MODE, P2V, STAGV, NFV, NCHV, 512); break;                                        \
+    case 256: BMQ_MARCH_CASE(MODE, P2V, STAGV, NFV, NCHV, 256); break;                                        \
+    case 128: BMQ_MARCH_CASE(MODE, P2V, STAGV, NFV, NCHV, 128); break;                                        \
+    default: BMQ_MARCH_CASE(MODE, P2V, STAGV, NFV, NCHV, 0); break;                                           \
+    }
+#define BMQ_MARCH_P2(MODE, STAGV, NFV, NCHV)                                                                  \
+    if (p2) { BMQ_MARCH_FIX(MODE, true, STAGV, NFV, NCHV) } else { BMQ_MARCH_FIX(MODE, false, STAGV, NFV, NCHV) }
+
+// one (NF, NCH) configuration over all staggerings; NF == 2 exists for centred fields only
+template <int MODE, int NF, int NCH>
+cudaError_t launch_march(cudaStream_t s, const Grid3 &g, KRange r, int stag, const MarchArgs<NF, NF * NCH> &a, const Map3 &m)
+{
+    if (r.kend <= r.kbeg) return cudaSuccess;
+    const int fi = g.ni + (stag == 1), fj = g.nj + (stag == 2);
+    const int kc = march_chunk(fi, fj, r.kend - r.kbeg);
+    const dim3 bl(32, BMQ_MARCH_BY, 1);
+    const dim3 gr((fi + 31) / 32, (fj + BMQ_MARCH_BY - 1) / BMQ_MARCH_BY, (r.kend - r.kbeg + kc - 1) / kc);
+    const int fix = march_fix_of(g);
+    const bool p2 = march_is_pow2_h(g);
+    if (NF == 2 && stag != 0) return cudaErrorInvalidValue;
+    if (stag == 0) {
+        BMQ_MARCH_P2(MODE, 0, NF, NCH)
+    } else if constexpr (NF == 1) {
+        if (stag == 1) { BMQ_MARCH_P2(MODE, 1, NF, NCH) }
+        else if (stag == 2) { BMQ_MARCH_P2(MODE, 2, NF, NCH) }
+        else { BMQ_MARCH_P2(MODE, 3, NF, NCH) }
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace bmq

@@ -49,6 +49,10 @@ unsigned long long bmq_kernel_launch_count(void);
  * row and plane pitches are compile-time constants (same arithmetic, 17 % fewer instructions); 0
  * switches them off so that tests can compare the two paths bit for bit.  Default: on. */
 int bmq_set_pitch_specialisation(int on);
+/* Testing knob.  The advect / error / apply / accumulate gathers run as z-marching column kernels
+ * (variant 1, default: a thread keeps the x-y-interpolated map planes of its column in registers) or as
+ * one windowed cell per thread (variant 0).  Same arithmetic, bit-identical results. */
+int bmq_set_gather_variant(int variant);
 
 /* ---- peer-memory plumbing for the z-slab halo exchange over NVLink (one process per GPU).
  * bmq_ipc_export: CUDA IPC handle (64 bytes) of the allocation `dev_ptr` is the base of;

@@ -104,14 +104,21 @@ def test_halo_overflow_grows_the_halo(cuda):
 def test_forty_frames_with_growing_displacement(cuda, world, blend):
     """The failure of round 1 (SCALE_r01: HaloTooNarrow at frame ~20): 40 free-running frames at
     CFL 1.5, so that the scalar mapper's z-displacement grows for up to 30 frames.  The halo starts
-    at 12 planes, narrower than what the run needs AND than the 16-plane slabs will allow to serve from
+    at 12 planes, narrower than what the run needs; the reach also exceeds what the 24- / 32-plane slabs can serve from
     the direct neighbour alone: it has to grow, and halos reach past the neighbouring slab.  Owned
     planes stay bit-identical to a single GPU; the widths follow the per-mapper displacement."""
     from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
-    ni, nj, nk, dt, frames = 32, 28, 64, 0.02, 40
+    ni, nj, nk, dt, frames = 32, 28, 96, 0.02, 40
     h = 1.0 / ni
+    # a z-directed jet w = sin^2(pi x) sin^2(pi y) (divergence free) on top of the plume's ring: map points
+    # travel up to 1.5 planes per frame, so the scalar maps reach tens of planes before they are reinitialised
     u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0)
-    u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
+    x = (np.arange(ni) / ni)[None, None, :]; y = (np.arange(nj) / nj)[None, :, None]
+    jet = (np.sin(np.pi * x) ** 2 * np.sin(np.pi * y) ** 2).astype(np.float32)
+    w = 0.02 * w / max(float(np.abs(w).max()), 1e-30) + np.broadcast_to(jet, w.shape)
+    u, v = 0.02 * u / float(np.abs(u).max()), 0.02 * v / float(np.abs(v).max())
+    u, v, w = scenes.scale_to_cfl(u, v, np.ascontiguousarray(w, dtype=np.float32), h, dt, 1.5)
+    u, v, w = [np.ascontiguousarray(a, dtype=np.float32) for a in (u, v, w)]
     single = BimocqAdvection3D(ni, nj, nk, h, blend)
     single.set_initial(u, v, w, rho, T)
     ranks = [zslab.CudaSlabRank(ni, nj, nk, h, blend, r, world, 12) for r in range(world)]
@@ -130,7 +137,7 @@ def test_forty_frames_with_growing_displacement(cuda, world, blend):
         widest = max(widest, st.stats["halo_used"])
         if frame % 8 == 7 or frame == frames - 1:
             _assert_owned_equal(ranks, single, nk, CHECK, frame)
-    assert widest > 12 and st.grow_count >= 1, (widest, st.grow_count)
+    assert widest > 24 and st.grow_count >= 1, (widest, st.grow_count)
     for r in ranks:
         r.close()
     single.close()
