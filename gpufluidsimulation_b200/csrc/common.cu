@@ -108,5 +108,7 @@ const char *bmq_version(void) { return "bimocq_b200 0.1 (sm_100a)"; }
 unsigned long long bmq_kernel_launch_count(void) { return bmq::kernel_launch_count(); }
 int bmq_set_pitch_specialisation(int on) { bmq::set_pitch_specialisation(on != 0); return BMQ_OK; }
 int bmq_set_gather_variant(int variant) { bmq::set_gather_variant(variant); return BMQ_OK; }
+int bmq_set_fast_division(int on) { bmq::set_fast_division(on != 0); return BMQ_OK; }
+int bmq_division_is_fast(float h, int nmax) { return bmq::division_is_fast(h, nmax) ? 1 : 0; }
 
 }  // extern "C"

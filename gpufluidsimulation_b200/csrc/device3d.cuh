@@ -16,8 +16,29 @@ namespace bmq {
 
 struct Grid3 {
     int ni, nj, nk;   // global cell counts
-    float h, inv_h;   // cell size; 1/h (exact when h is a power of two)
+    float h;          // cell size
+    float inv_h;      // RN(1/h) (exact when h is a power of two); NEGATED when the three-instruction division
+                      // div_h() has not been verified for this h (kernels3d.cu:make_grid) -> IEEE division
 };
+
+// p / h, correctly rounded, for the one divisor a launch ever has.  The reference divides (pos / h,
+// GPU_kernel.cu:46-51); an IEEE division is ~10 instructions plus a slow-path call.  With y = RN(1/h):
+//   q0 = RN(p y);  r = p - h q0 (exact, one fma);  q = RN(q0 + r y)
+// is the correctly rounded quotient (Markstein's division step) for all but pathological divisors, as long as
+// the residual does not underflow; instead of relying on the theorem, make_grid() checks the sequence against
+// __fdiv_rn for EVERY float p in {0} U [2^-100, largest position], once per h, on the device, and hands the
+// kernels a negated inv_h if a single one differs.  |p| below 2^-100 (never a position in practice; the
+// residual would be subnormal there) takes the IEEE division.
+#define BMQ_DIV_TINY 7.888609052e-31f   /* 2^-100 */
+__device__ __forceinline__ float div_h(float p, float h, float inv_h)
+{
+    if (inv_h > 0.f && (fabsf(p) >= BMQ_DIV_TINY || p == 0.f)) {
+        const float q0 = __fmul_rn(p, inv_h);
+        const float r = __fmaf_rn(-h, q0, p);
+        return __fmaf_rn(r, inv_h, q0);
+    }
+    return __fdiv_rn(p, h);
+}
 
 // FIX != 0: the x and y extents are the compile-time constant FIX, so that row and plane pitches of
 // every gather become immediates of the load instructions instead of 64-bit address arithmetic.
@@ -36,7 +57,7 @@ struct Frac {
 template <bool P2>
 __device__ __forceinline__ Frac split(float p, float h, float inv_h)
 {
-    float q = P2 ? p * inv_h : __fdiv_rn(p, h);
+    float q = P2 ? p * inv_h : div_h(p, h, inv_h);
     float fl = floorf(q);
     Frac r;
     r.i = (int)fl;
@@ -380,7 +401,7 @@ struct AxisW {
             fp = STAGGERED ? 0.75f : 0.25f;
         } else {
             const float q = 0.25f * h;
-            const float qm = __fdiv_rn(c_pos - q, h), qp = __fdiv_rn(c_pos + q, h);
+            const float qm = div_h(c_pos - q, h, inv_h), qp = div_h(c_pos + q, h, inv_h);
             fm = qm - floorf(qm);
             fp = qp - floorf(qp);
         }

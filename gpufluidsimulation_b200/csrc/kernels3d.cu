@@ -11,10 +11,15 @@
 #include "device3d.cuh"
 
 #include <atomic>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace bmq {
 
 static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<bool> g_fast_division{true};   // testing knob, see bmq_set_fast_division
 unsigned long long kernel_launch_count() { return g_launches.load(); }
 static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -29,12 +34,59 @@ static inline bool is_pow2_h(const Grid3 &g)
     return m == 0.5f && (long long)nmax * 4 + 8 < (1ll << 24);
 }
 
+// ---- exhaustive check of div_h (device3d.cuh) for one divisor: every float p in [0, p_max]
+// (div_h takes the three-instruction path for p == 0 and p >= 2^-100, which is what gets verified)
+__global__ void __launch_bounds__(256) k_verify_div(float h, float inv_h, unsigned last_bits, unsigned *mismatches)
+{
+    unsigned bad = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= last_bits;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float p = __uint_as_float((unsigned)b);       // tiny p: div_h itself falls back to IEEE division there
+        bad += __float_as_uint(div_h(p, h, inv_h)) != __float_as_uint(__fdiv_rn(p, h));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// true when div_h reproduces IEEE division by h for every float in [0, p_max] (the sequence is odd in p, so
+// negative positions are covered).  Checked once per (h, range) on the current device: ~1e9 quotients, a few ms.
+static bool division_verified(float h, float p_max)
+{
+    static std::mutex mu;
+    static std::map<unsigned, std::pair<float, bool>> cache;    // bits of h -> (verified range, outcome)
+    unsigned key;
+    memcpy(&key, &h, sizeof key);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end() && (it->second.first >= p_max || !it->second.second)) return it->second.second;
+    bool ok = false;
+    unsigned *d_bad = nullptr, h_bad = 1, last;
+    memcpy(&last, &p_max, sizeof last);
+    if (cudaMalloc(&d_bad, sizeof(unsigned)) == cudaSuccess) {
+        if (cudaMemset(d_bad, 0, sizeof(unsigned)) == cudaSuccess) {
+            k_verify_div<<<148 * 8, 256>>>(h, 1.0f / h, last, d_bad);
+            if (cudaMemcpy(&h_bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost) == cudaSuccess) ok = h_bad == 0;
+        }
+        cudaFree(d_bad);
+    }
+    if (cudaGetLastError() != cudaSuccess) ok = false;      // no device, launch failure: IEEE division, loudly elsewhere
+    else cache[key] = std::make_pair(p_max, ok);
+    return ok;
+}
+
 Grid3 make_grid(int ni, int nj, int nk, float h)
 {
     Grid3 g;
     g.ni = ni; g.nj = nj; g.nk = nk; g.h = h; g.inv_h = 1.0f / h;
+    if (!is_pow2_h(g)) {
+        // positions stay inside the clamped domain plus one DMC reach; verify four times the domain
+        int nmax = ni > nj ? ni : nj;
+        nmax = nmax > nk ? nmax : nk;
+        if (!g_fast_division.load(std::memory_order_relaxed) || !division_verified(h, 4.0f * (float)(nmax + 8) * h)) g.inv_h = -g.inv_h;
+    }
     return g;
 }
+void set_fast_division(bool on) { g_fast_division.store(on); }
+bool division_is_fast(float h, int nmax) { return make_grid(nmax, nmax, nmax, h).inv_h > 0.f; }
 
 // CTA shape (32, BMQ_BY, BMQ_BZ); default 32x4x1 = 128 threads.  A CTA that spans several z-planes shares the
 // k-1/k/k+1 planes of the map windows and of the near-identity field gathers in L1.

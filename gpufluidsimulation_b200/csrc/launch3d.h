@@ -29,6 +29,8 @@ Grid3 make_grid(int ni, int nj, int nk, float h);
 unsigned long long kernel_launch_count();
 void set_pitch_specialisation(bool on);   // testing knob, see bmq_set_pitch_specialisation
 void set_gather_variant(int v);           // testing knob, see bmq_set_gather_variant
+void set_fast_division(bool on);          // testing knob, see bmq_set_fast_division
+bool division_is_fast(float h, int nmax);
 // z-marching gather kernels (march_*.cu); same contracts as launch_advect / _error / _cumulate / _apply_clamp
 // with is_point == false
 cudaError_t launch_advect_march(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, float *const *out,

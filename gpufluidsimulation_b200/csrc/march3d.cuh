@@ -22,8 +22,6 @@
 // The apply kernel's 27-neighbour extrema clamp (clampExtrema_kernel, GPU_kernel.cu:146-167) marches the
 // same way: min/max of the 3x3 neighbourhood per plane are carried, 9 loads per cell instead of 27.
 #pragma once
-#include <type_traits>
-
 #include "launch3d.h"
 #include "device3d.cuh"
 
@@ -36,9 +34,6 @@ enum { GM_ADVECT = 0, GM_ERROR = 1, GM_CUMULATE = 2, GM_APPLY = 3 };
 #endif
 #ifndef BMQ_MARCH_MINBLOCKS
 #define BMQ_MARCH_MINBLOCKS 6   // x 128 threads: 24 warps per SM at <= 80 registers (sweep: profiles/r2_march_variants.md)
-#endif
-#ifndef BMQ_MARCH_UNROLL
-#define BMQ_MARCH_UNROLL 0      // 1: k loop unrolled by the ring period (no register moves, but 3-6x the code: slower); 0: one cell per iteration
 #endif
 #ifndef BMQ_MARCH_PREFETCH
 #define BMQ_MARCH_PREFETCH 1    // 1 / 2: prefetch the next cell's new map plane and field plane into L1 / L2
@@ -122,11 +117,11 @@ __device__ __forceinline__ void z_combine(const PlaneXY &Pa, const PlaneXY &Pb, 
 // Positions reach it clamped: in cells when GRID (power-of-two h), as world positions otherwise.  Returns
 // (position - field origin) / h, the reference's `pos / h` of sample_buffer (GPU_kernel.cu:46-51).
 template <bool GRID>
-__device__ __forceinline__ float to_cells(float p, float off_world, float off_grid, float h)
+__device__ __forceinline__ float to_cells(float p, float off_world, float off_grid, float h, float inv_h)
 {
     // GRID: p is already in cells; the staggering offset (+1/2) is the only arithmetic left
     if (GRID) return off_grid != 0.f ? p + off_grid : p;
-    return __fdiv_rn(off_world != 0.f ? p - off_world : p, h);
+    return div_h(off_world != 0.f ? p - off_world : p, h, inv_h);
 }
 
 struct Split2 {
@@ -260,30 +255,17 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
     az.init(0.f, h, g.inv_h);     // power-of-two h: constants; otherwise re-initialised per cell
     const int sy = g.ni, sz = g.ni * g.nj;
     const int mbase = (i - 1) + sy * (j - 1);
-    PlaneXY Px[3], Py[3], Pz[3];  // ring of carried map planes: z node n of the cell run by body<R> is slot (R + n) % NZ
+    PlaneXY Px[3], Py[3], Pz[3];  // map planes of the current window (z nodes 0..NZ-1)
     Plane9 M[NF][3];              // apply: ring of 3x3 extrema of f_adv planes k-1, k, k+1
     const bool gathers = gij && ka < kb;
     const int kfirst = MODE == GM_APPLY ? kc0 : ka, klast = MODE == GM_APPLY ? kc1 : kb;
 
-    // One cell.  R = (k - kfirst) % PERIOD selects, at compile time, which ring slots hold the window planes,
-    // so that the carried planes never move between registers.
-#if BMQ_MARCH_PREFETCH == 3
-    // experiment: prefetch by REAL loads whose values are consumed one cell later (proves / disproves that the
-    // L1-miss latency of the new planes is what the cells wait for)
-    float pf_v[16];
-    int pf_sink = 0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) pf_v[q] = 0.f;
-    const int pf_dx = threadIdx.x == 0 ? 0 : 2;
-#endif
-    auto body = [&](auto Rtag, int k) {
-        constexpr int R = decltype(Rtag)::value;
-#if BMQ_MARCH_PREFETCH == 3
-#pragma unroll
-        for (int q = 0; q < 16; ++q) pf_sink |= __float_as_int(pf_v[q]);
-#endif
-        constexpr int S0 = R % NZ, S1 = (R + 1) % NZ, S2 = (R + 2) % NZ;     // slots of z nodes 0, 1, 2
-        constexpr int SN = NZ == 3 ? S2 : S1;                                // slot the new plane goes to
+    // One cell: z node n of its window is Px/Py/Pz[n]; the newest plane is loaded here, the others are carried.
+    // (Unrolling the k loop by the ring period instead of moving the planes down was measured: 3-6x the code,
+    // 10 % slower -- profiles/r2_march_variants.md.)
+    auto body = [&](int k) {
+        constexpr int S0 = 0, S1 = 1, S2 = NZ == 3 ? 2 : 0;
+        constexpr int SN = NZ - 1;                                           // slot the new plane goes to
         const int idx = col + fplane * k;
         const bool gk = MODE != GM_APPLY || (gathers && k >= ka && k < kb);
         float sum[NS], val[NS];
@@ -298,15 +280,9 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
                 // the plane the NEXT cell of this column will load: rows j-1..j+1 (lanes cover i-1..i+30, +1 the rest)
 #pragma unroll
                 for (int y = 0; y < (STAG == 2 ? 2 : 3); ++y) {
-#if BMQ_MARCH_PREFETCH == 3
-                    pf_v[3 * y + 0] = __ldg(m.x + onew + sz + y * sy + pf_dx);
-                    pf_v[3 * y + 1] = __ldg(m.y + onew + sz + y * sy + pf_dx);
-                    pf_v[3 * y + 2] = __ldg(m.z + onew + sz + y * sy + pf_dx);
-#else
                     prefetch_line(m.x + onew + sz + y * sy + 1);
                     prefetch_line(m.y + onew + sz + y * sy + 1);
                     prefetch_line(m.z + onew + sz + y * sy + 1);
-#endif
                 }
             }
             const float cz = DZ ? fmaf(h, (float)k, oz) : __fmul_rn(h, (float)k);
@@ -331,12 +307,12 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 float2 qx, qy, qz;
-                qx.x = to_cells<P2>(clampf(px[ii].x, lo, hix), ox, DX * 0.5f, h);
-                qx.y = to_cells<P2>(clampf(px[ii].y, lo, hix), ox, DX * 0.5f, h);
-                qy.x = to_cells<P2>(clampf(py[ii].x, lo, hiy), oy, DY * 0.5f, h);
-                qy.y = to_cells<P2>(clampf(py[ii].y, lo, hiy), oy, DY * 0.5f, h);
-                qz.x = to_cells<P2>(clampf(pz[ii].x, lo, hiz), oz, DZ * 0.5f, h);
-                qz.y = to_cells<P2>(clampf(pz[ii].y, lo, hiz), oz, DZ * 0.5f, h);
+                qx.x = to_cells<P2>(clampf(px[ii].x, lo, hix), ox, DX * 0.5f, h, g.inv_h);
+                qx.y = to_cells<P2>(clampf(px[ii].y, lo, hix), ox, DX * 0.5f, h, g.inv_h);
+                qy.x = to_cells<P2>(clampf(py[ii].x, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
+                qy.y = to_cells<P2>(clampf(py[ii].y, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
+                qz.x = to_cells<P2>(clampf(pz[ii].x, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
+                qz.y = to_cells<P2>(clampf(pz[ii].y, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
                 const Split2 spx = split2(qx), spy = split2(qy), spz = split2(qz);
                 float s0[NS];
                 gather_pair<NS>(a.src, fi, fplane, spx, spy, spz, s0, late[ii]);
@@ -347,22 +323,17 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
             for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
                 for (int f = 0; f < NS; ++f) sum[f] = fmaf(wgt[f], late[ii][f], sum[f]);
-            const float qcx = to_cells<P2>(clampf(ccx, lo, hix), ox, DX * 0.5f, h);
-            const float qcy = to_cells<P2>(clampf(ccy, lo, hiy), oy, DY * 0.5f, h);
-            const float qcz = to_cells<P2>(clampf(ccz, lo, hiz), oz, DZ * 0.5f, h);
+            const float qcx = to_cells<P2>(clampf(ccx, lo, hix), ox, DX * 0.5f, h, g.inv_h);
+            const float qcy = to_cells<P2>(clampf(ccy, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
+            const float qcz = to_cells<P2>(clampf(ccz, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
             int zi;
             const int oc = gather_one<NS>(a.src, fi, fplane, qcx, qcy, qcz, val, zi);
             if (BMQ_MARCH_PREFETCH && k + 1 < kb && zi + 2 < fk) {
                 // the field plane the next cell's samples will newly touch: two planes above the centre sample's cell
 #pragma unroll
                 for (int f = 0; f < NS; ++f) {
-#if BMQ_MARCH_PREFETCH == 3
-                    pf_v[9 + 2 * f] = __ldg(a.src[f] + oc + 2 * fplane);
-                    pf_v[10 + 2 * f] = __ldg(a.src[f] + oc + 2 * fplane + fi);
-#else
                     prefetch_line(a.src[f] + oc + 2 * fplane);
                     prefetch_line(a.src[f] + oc + 2 * fplane + fi);
-#endif
                 }
             }
         }
@@ -384,8 +355,7 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
                 a.out[f][idx] = t;
             }
         } else {
-            // extrema ring: planes k-1, k, k+1 sit in slots R % 3, (R + 1) % 3, (R + 2) % 3
-            constexpr int Q0 = R % 3, Q1 = (R + 1) % 3, Q2 = (R + 2) % 3;
+            constexpr int Q0 = 0, Q1 = 1, Q2 = 2;     // extrema of planes k-1, k, k+1
             const bool clamps = k > 0 && k < fk - 1;
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
@@ -402,66 +372,34 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
         }
     };
 
-    // unrolled by the ring period so that slot indices are compile-time constants (no register moves):
-    // NZ for the gather-only kernels; the apply kernel also rotates a 3-slot extrema ring -> 6
-    constexpr int PERIOD = !BMQ_MARCH_UNROLL ? 1 : MODE == GM_APPLY ? 6 : NZ;
     // carried planes at loop entry: the window of the first gathering cell minus its newest plane
     if (gathers) {
         const int o0 = mbase + sz * (ka - 1);
-        const int r0 = (ka - kfirst) % PERIOD;       // cell ka is run by body<r0>: its z node n sits in slot (r0 + n) % NZ
 #pragma unroll
         for (int n = 0; n < NZ - 1; ++n) {
-            const PlaneXY qx = plane_xy<P2, STAG>(m.x + o0 + n * sz, sy, ax, ay);
-            const PlaneXY qy = plane_xy<P2, STAG>(m.y + o0 + n * sz, sy, ax, ay);
-            const PlaneXY qz = plane_xy<P2, STAG>(m.z + o0 + n * sz, sy, ax, ay);
-#pragma unroll
-            for (int s = 0; s < NZ; ++s)
-                if ((r0 + n) % NZ == s) { Px[s] = qx; Py[s] = qy; Pz[s] = qz; }
+            Px[n] = plane_xy<P2, STAG>(m.x + o0 + n * sz, sy, ax, ay);
+            Py[n] = plane_xy<P2, STAG>(m.y + o0 + n * sz, sy, ax, ay);
+            Pz[n] = plane_xy<P2, STAG>(m.z + o0 + n * sz, sy, ax, ay);
         }
     }
     if (MODE == GM_APPLY) {
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-            M[f][1] = plane9(a.aux[f] + col + fplane * kc0, fi);       // plane k = kc0: slot Q1 of body<0>
+            M[f][1] = plane9(a.aux[f] + col + fplane * kc0, fi);
             M[f][0] = kc0 > 0 ? plane9(a.aux[f] + col + fplane * (kc0 - 1), fi) : M[f][1];
         }
     }
-    int k = kfirst;
-    if (!BMQ_MARCH_UNROLL) {
 #pragma unroll 1
-        for (; k < klast; ++k) {
-            body(std::integral_constant<int, 0>{}, k);
-            if (MODE != GM_APPLY || (gathers && k >= ka && k < kb)) {
-                Px[0] = Px[1]; Py[0] = Py[1]; Pz[0] = Pz[1];
-                if (NZ == 3) { Px[1] = Px[2]; Py[1] = Py[2]; Pz[1] = Pz[2]; }
-            }
-            if (MODE == GM_APPLY) {
+    for (int k = kfirst; k < klast; ++k) {
+        body(k);
+        if (MODE != GM_APPLY || (gathers && k >= ka && k < kb)) {
+            Px[0] = Px[1]; Py[0] = Py[1]; Pz[0] = Pz[1];
+            if (NZ == 3) { Px[1] = Px[2]; Py[1] = Py[2]; Pz[1] = Pz[2]; }
+        }
+        if (MODE == GM_APPLY) {
 #pragma unroll
-                for (int f = 0; f < NF; ++f) { M[f][0] = M[f][1]; M[f][1] = M[f][2]; }
-            }
+            for (int f = 0; f < NF; ++f) { M[f][0] = M[f][1]; M[f][1] = M[f][2]; }
         }
-#if BMQ_MARCH_PREFETCH == 3
-        if (pf_sink == 0x7fc12345) a.out[0][0] = 0.f;
-#endif
-        return;
-    }
-#pragma unroll 1
-    for (; k + PERIOD <= klast; k += PERIOD) {
-        body(std::integral_constant<int, 0>{}, k);
-        body(std::integral_constant<int, 1>{}, k + 1);
-        if (PERIOD > 2) body(std::integral_constant<int, 2>{}, k + 2);
-        if (PERIOD > 3) {
-            body(std::integral_constant<int, 3>{}, k + 3);
-            body(std::integral_constant<int, 4>{}, k + 4);
-            body(std::integral_constant<int, 5>{}, k + 5);
-        }
-    }
-    if (k < klast) body(std::integral_constant<int, 0>{}, k);
-    if (k + 1 < klast) body(std::integral_constant<int, 1>{}, k + 1);
-    if (PERIOD > 3) {
-        if (k + 2 < klast) body(std::integral_constant<int, 2>{}, k + 2);
-        if (k + 3 < klast) body(std::integral_constant<int, 3>{}, k + 3);
-        if (k + 4 < klast) body(std::integral_constant<int, 4>{}, k + 4);
     }
 }
 

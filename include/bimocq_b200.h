@@ -53,6 +53,14 @@ int bmq_set_pitch_specialisation(int on);
  * (variant 1, default: a thread keeps the x-y-interpolated map planes of its column in registers) or as
  * one windowed cell per thread (variant 0).  Same arithmetic, bit-identical results. */
 int bmq_set_gather_variant(int variant);
+/* Division by the cell size.  The reference computes pos / h (GPU_kernel.cu:46-51); when h is not a power
+ * of two the kernels use a three-instruction sequence (multiply by RN(1/h), exact residual, correction) that
+ * the library has checked against IEEE division for EVERY float a position can take, once per h, on the
+ * device; if a single quotient differs (or with bmq_set_fast_division(0), a testing knob that applies to
+ * handles and grids created afterwards) they use IEEE division.  bmq_division_is_fast reports the outcome for
+ * a grid of nmax cells per axis (1 = fast sequence in use; power-of-two h: always 1, no division at all). */
+int bmq_set_fast_division(int on);
+int bmq_division_is_fast(float h, int nmax);
 
 /* ---- peer-memory plumbing for the z-slab halo exchange over NVLink (one process per GPU).
  * bmq_ipc_export: CUDA IPC handle (64 bytes) of the allocation `dev_ptr` is the base of;
