@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- BiMocq^2 3D advection throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload plume512|plume256|plume128|rings256]
+                    [--domain-length 1.0|0.2] [--impl reference]
 
 A "step" is one pass of the advection hot path over the whole grid: phase A (max velocity, DMC
 backward + RK3 forward map update for both mappers, advect + compensate + clamp velocity, density
@@ -15,6 +16,13 @@ state).  Inputs are synthetic (closed-form vortex ring + smooth ball), resident 
 timed region; every field is 537 MB, larger than the 126 MB L2, so no L2 flush is needed between
 iterations.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
 max over ranks.
+
+The headline line uses the power-of-two cell size h = 1/n (exact-multiplication path); the same run also
+reports, as extra keys at N=1: `general_h` (the same workload at the reference scene's h = 0.2/n,
+bimocq3D/main.cpp:36-38: division path), `workloads` (the other BASELINE configs: plume 128^3, rings 256^3),
+`reference_gpu` (the reference's own kernels, oracle/_ref/libref3d.so, through its call sequence on the same
+B200: the kernel to beat), `bimocq2d` (1024^2 on the GPU, plus the reference's own 2D CPU code at 256^2 over
+100 steps) and `cpu_baseline` (the C restatement of the 3D kernels on the host cores).
 
 Output: ONE JSON line (see the keys below).  `--impl reference` times the CPU oracle port of the
 reference CUDA kernels (the 3D reference has no CPU advection path) on the host cores.
@@ -39,6 +47,21 @@ METRIC = "BiMocq2 3D advection cell-updates/sec"
 UNIT = "cell-updates/s"
 DT = 0.02
 CFL = 1.5
+# BASELINE.json configs[2..4] (+ a 256^3 plume for quick runs): grid size, scene, description
+WORKLOADS = {
+    "plume512": (512, "plume", "BiMocq3D smoke plume 512^3 (velocity + density + temperature)"),
+    "plume256": (256, "plume", "BiMocq3D smoke plume 256^3 (velocity + density + temperature)"),
+    "plume128": (128, "plume", "BiMocq3D smoke plume 128^3 (velocity + density + temperature)"),
+    "rings256": (256, "rings", "BiMocq3D leapfrogging vortex rings 256^3 (velocity + two ring-core scalars)"),
+}
+
+
+def make_scene(kind, n, L, xp, device=None):
+    from gpufluidsimulation_b200 import scenes
+    f = scenes.smoke_plume if kind == "plume" else scenes.leapfrog_rings
+    u, v, w, rho, T = f(n, n, n, L, xp=xp, device=device) if device is not None else f(n, n, n, L)
+    u, v, w = scenes.scale_to_cfl(u, v, w, L / n, DT, CFL)
+    return u, v, w, rho, T
 
 
 def alg_bytes_per_cell(n_sub: float) -> float:
@@ -147,7 +170,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BiMocq3D smoke plume {args.size}^3 (velocity + density + temperature)",
+        "config": {"workload": WORKLOADS[args.workload][2],
                    "timed_on": f"bounded sample: same scene at {n}^3, CFL {CFL}, dt {DT}"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n}^3 plume, {args.steps} steps after {args.warmup} warm-up; the 3D reference "
@@ -176,6 +199,92 @@ def bind_to_gpu_numa_node(local: int) -> None:
         print(f"bench: NUMA binding skipped ({exc})", file=sys.stderr)
 
 
+def alg_bytes_per_launch(n, world):
+    """DESIGN.md "Kernels": fp32 arrays a launch of the stage's kernel must read or write once (per rank)."""
+    fu, fc, own = (n + 1) * n * n, n * n * n, 1.0 / world
+    return {
+        "accumulate_velocity": ("k_march<cumulate,NF=1,NCH=2>", 7 * 4 * fu * own),   # psi3 + d_ext + d_proj + init R/W
+        "advect_velocity": ("k_march<advect,NF=1>", 5 * 4 * fu * own),               # chi3 + init + out
+        "error_velocity": ("k_march<error,NF=1>", 6 * 4 * fu * own),                 # psi3 + f_adv + init + e0
+        "apply_velocity": ("k_march<apply,NF=1>", 6 * 4 * fu * own),                 # chi3 + e0 + f_adv + out
+        "advect_scalars": ("k_march<advect,NF=2>", 7 * 4 * fc * own),
+        "error_scalars": ("k_march<error,NF=2>", 9 * 4 * fc * own),
+        "apply_scalars": ("k_march<apply,NF=2>", 9 * 4 * fc * own),
+        "accumulate_scalars": ("k_march<cumulate,NF=2,NCH=1>", 9 * 4 * fc * own),
+        "dmc_backward": ("k_dmc<NMAP=2>", 15 * 4 * fc * own),
+        "forward": ("k_forward<NMAP=2>", 15 * 4 * fc * own),
+        "distortion": ("k_estimate<NMAP=2>", 12 * 4 * fc * own),
+    }
+
+
+def make_solver(n, L, world, rank, args):
+    from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
+    h = L / n
+    if world > 1:
+        from gpufluidsimulation_b200.zslab import ZSlabAdvection3D
+        return ZSlabAdvection3D(n, n, n, h, 1.0, rank=rank, world=world, halo=args.halo, transport=args.transport, cfl_frame=CFL)
+    return BimocqAdvection3D(n, n, n, h, 1.0)
+
+
+def timed_steps(solver, torch, dist, world, dev, steps, warmup, beta=1e-2, on_timed_start=None):
+    """`warmup` untimed steps, then `steps` steps between two barriers + synchronisations, timed with CUDA
+    events on the launching stream; returns (ms for all steps (max over ranks), mean n_sub, stage timings,
+    next frame)."""
+    def step(frame):
+        solver.advect(frame, DT)
+        solver.apply_buoyancy(beta, DT)      # caller stand-in between the phases (reference buoyancy on v)
+        solver.accumulate(frame, DT)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frame = 0
+    for _ in range(warmup):
+        step(frame); frame += 1
+    barrier()
+    solver.timing_enable(True)
+    solver.timing_read()
+    if on_timed_start:
+        on_timed_start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    nsub = []
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step(frame); frame += 1
+        nsub.append(solver.stats()["n_substeps"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stage = solver.timing_read()
+    solver.timing_enable(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, float(np.mean(nsub)), stage, frame
+
+
+def short_run(torch, dist, world, rank, dev, args, kind, n, L, steps=8, warmup=3):
+    """One of the other workloads, briefly: ms/step, cell-updates/s, whole-step roofline fraction."""
+    solver = make_solver(n, L, world, rank, args)
+    solver.set_initial_device(*make_scene(kind, n, L, torch, dev))
+    torch.cuda.empty_cache()
+    ms, n_sub, _, _ = timed_steps(solver, torch, dist, world, dev, steps, warmup)
+    st = solver.stats()
+    solver.close()
+    torch.cuda.empty_cache()
+    rate = n ** 3 * steps / (ms * 1e-3)
+    peak, _ = measured_peak()
+    out = {"grid": [n, n, n], "h": f"{L}/{n}", "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "cell_updates_per_s": rate,
+           "n_sub_mean": n_sub, "hbm_roofline_frac": alg_bytes_per_cell(n_sub) * rate / 1e9 / (peak * world)}
+    if world > 1:
+        out["halo_vel_scalar_allocated"] = [st.get("halo_vel"), st.get("halo_scalar"), st.get("halo_allocated")]
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -189,95 +298,37 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    from gpufluidsimulation_b200 import load_library, scenes
-    from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
+    from gpufluidsimulation_b200 import load_library
 
     lib = load_library()
-    n = args.size
-    h = 1.0 / n
+    n, kind, desc = WORKLOADS[args.workload]
+    if args.size:
+        n, desc = args.size, desc.replace(str(WORKLOADS[args.workload][0]) + "^3", f"{args.size}^3")
+    L = args.domain_length
     cells = n ** 3
-
-    if world > 1:
-        from gpufluidsimulation_b200.zslab import ZSlabAdvection3D
-        solver = ZSlabAdvection3D(n, n, n, h, 1.0, rank=rank, world=world, halo=args.halo, transport=args.transport,
-                                  cfl_frame=CFL)
-    else:
-        solver = BimocqAdvection3D(n, n, n, h, 1.0)
-
-    u, v, w, rho, T = scenes.smoke_plume(n, n, n, 1.0, xp=torch, device=dev)
-    u, v, w = scenes.scale_to_cfl(u, v, w, h, DT, CFL)
-    solver.set_initial_device(u, v, w, rho, T)
-    del u, v, w, rho, T
+    solver = make_solver(n, L, world, rank, args)
+    solver.set_initial_device(*make_scene(kind, n, L, torch, dev))
     torch.cuda.empty_cache()
 
-    beta = 1e-2
-
-    def forcing():
-        # caller stand-in between the phases: reference buoyancy (GPU_kernel.cu:804-823) on v
-        solver.apply_buoyancy(beta, DT)
-
-    def step(frame):
-        solver.advect(frame, DT)
-        forcing()
-        solver.accumulate(frame, DT)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    frame = 0
-    for _ in range(args.warmup):
-        step(frame); frame += 1
-    barrier()
-    if getattr(solver, "stepper", None) is not None:
-        solver.stepper.prof = {}
-    solver.timing_enable(True)
-    solver.timing_read()
-    launches0 = lib.bmq_kernel_launch_count()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    nsub = []
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step(frame); frame += 1
-        nsub.append(solver.stats()["n_substeps"])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    launches0 = [0]
+
+    def on_timed_start():
+        if getattr(solver, "stepper", None) is not None:
+            solver.stepper.prof = {}
+        launches0[0] = lib.bmq_kernel_launch_count()
+        if rank == 0:
+            sampler.start()
+
+    ms, n_sub, stage, frame = timed_steps(solver, torch, dist, world, dev, args.steps, args.warmup, on_timed_start=on_timed_start)
     clocks = sampler.stop() if rank == 0 else None
-    launches = lib.bmq_kernel_launch_count() - launches0
-    stage = solver.timing_read()
-    solver.timing_enable(False)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    launches = lib.bmq_kernel_launch_count() - launches0[0]
     ms_per_step = ms / args.steps
     value = cells * args.steps / (ms * 1e-3)
-    n_sub = float(np.mean(nsub))
 
     # ---- roofline of the dominant kernel (largest share of the step), live CUDA-event timing
     peak, peak_src = measured_peak()
-    faces = {"u": (n + 1) * n * n, "c": n * n * n}
-    own_frac = 1.0 / world
-    # algorithmic bytes per LAUNCH (DESIGN.md "Kernels"): fp32 arrays a launch must read/write once
-    alg = {
-        "accumulate_velocity": ("k_cumulate_win<NF=1,NCH=2>", 7 * 4 * faces["u"] * own_frac),   # psi3 + d_ext + d_proj + init R/W
-        "advect_velocity": ("k_advect_win<NF=1>", 5 * 4 * faces["u"] * own_frac),               # chi3 + init + out
-        "error_velocity": ("k_error_win<NF=1>", 6 * 4 * faces["u"] * own_frac),                 # psi3 + f_adv + init + e0
-        "apply_velocity": ("k_apply_clamp_win<NF=1>", 6 * 4 * faces["u"] * own_frac),           # chi3 + e0 + f_adv + out
-        "advect_scalars": ("k_advect_win<NF=2>", 7 * 4 * faces["c"] * own_frac),
-        "error_scalars": ("k_error_win<NF=2>", 9 * 4 * faces["c"] * own_frac),
-        "apply_scalars": ("k_apply_clamp_win<NF=2>", 9 * 4 * faces["c"] * own_frac),
-        "accumulate_scalars": ("k_cumulate_win<NF=2,NCH=1>", 9 * 4 * faces["c"] * own_frac),
-        "dmc_backward": ("k_dmc<NMAP=2>", 15 * 4 * faces["c"] * own_frac),
-        "forward": ("k_forward<NMAP=2>", 15 * 4 * faces["c"] * own_frac),
-        "distortion": ("k_estimate<NMAP=2>", 12 * 4 * faces["c"] * own_frac),
-    }
+    alg = alg_bytes_per_launch(n, world)
     launches_per_span = {"accumulate_velocity": 3, "advect_velocity": 3, "error_velocity": 3, "apply_velocity": 3}
     shares = {k: v[0] for k, v in stage.items() if v[1] > 0}
     total_stage_ms = sum(shares.values())
@@ -285,33 +336,44 @@ def run_gpu(args):
     top_launches = stage[top][1] * launches_per_span.get(top, 1)
     top_ms_per_launch = stage[top][0] / top_launches
     achieved = alg[top][1] / (top_ms_per_launch * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tfile = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-    if os.path.exists(tfile):
+    if os.path.exists(tfile) and n == 512:
         try:
-            traffic = json.load(open(tfile)).get(alg[top][0])
+            rec = json.load(open(tfile))
+            traffic = rec.get(alg[top][0])
+            traffic_src = rec.get("source", "imported from an ncu --set full capture under profiles/ (not measured in this run)")
+            if traffic is not None:
+                traffic = traffic / world
         except Exception:
             traffic = None
+    whole_gbs = alg_bytes_per_cell(n_sub) * value / 1e9
     roofline = {"bound": "hbm", "kernel": alg[top][0], "stage": top, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "ms_per_launch": top_ms_per_launch, "share_of_step": stage[top][0] / total_stage_ms,
                 "alg_bytes_per_launch": alg[top][1],
+                # whole job: all ranks' bytes over the max-over-ranks time, against N GPUs' worth of HBM
                 "whole_step": {"alg_bytes_per_cell_update": alg_bytes_per_cell(n_sub), "n_sub": n_sub,
-                               "achieved_gbs": alg_bytes_per_cell(n_sub) * value / 1e9,
-                               "frac": alg_bytes_per_cell(n_sub) * value / 1e9 / peak},
+                               "achieved_gbs": whole_gbs, "peak_gbs": peak * world, "frac": whole_gbs / (peak * world)},
                 "stage_ms_per_step": {k: round(v / args.steps, 4) for k, v in shares.items()}}
 
     line = None
     if rank == 0:
+        par = "single GPU"
+        if world > 1:
+            st = solver.stats()
+            par = (f"z-slab x{world}, halo {solver.halo} planes allocated (grown {solver.stepper.grow_count}x; last step exchanged "
+                   f"{st.get('halo_vel')} velocity-mapper / {st.get('halo_scalar')} scalar-mapper planes), exchange={solver.transport}")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BiMocq3D smoke plume {n}^3 (velocity + density + temperature), maps + 3 velocity "
-                                   "components + 2 scalars per step",
-                       "grid": [n, n, n], "dt": DT, "cfl_frame": CFL, "n_sub_mean": n_sub, "blend_coeff": 1.0,
-                       "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo {solver.halo} planes allocated (grown {solver.stepper.grow_count}x), exchange={solver.transport}",
-                       "l2_policy": "inputs larger than L2 (537 MB per field vs 126 MB L2), no flush needed"},
+            "config": {"workload": f"{desc}, maps + 3 velocity components + 2 scalars per step",
+                       "grid": [n, n, n], "h": f"{L}/{n}" + (" (power of two: exact-multiplication path)" if L == 1.0 else
+                                                          " (the reference scene's cell size: division path)"),
+                       "dt": DT, "cfl_frame": CFL, "n_sub_mean": n_sub, "blend_coeff": 1.0, "parallelism": par,
+                       "l2_policy": f"inputs larger than L2 ({4 * n ** 3 / 1e6:.0f} MB per field vs 126 MB L2), no flush needed"
+                                    if n >= 512 else f"{4 * n ** 3 / 1e6:.0f} MB per field, ~60 fields: working set larger than the 126 MB L2"},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         }
 
@@ -327,28 +389,109 @@ def run_gpu(args):
     elif line is not None:
         line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "note": "skipped (--no-e2e)"}
+    if world > 1 and rank == 0 and getattr(solver, "stepper", None) is not None and solver.stepper.profile:
+        print("ZSLAB_PROFILE", {k: round(v, 4) for k, v in solver.stepper.prof.items()}, file=sys.stderr)
+    solver.close()
+    del solver
+    torch.cuda.empty_cache()
 
-    if world == 1 and rank == 0 and not args.no_2d:
-        try:
-            line["bimocq2d"] = measure_2d(torch)
-        except Exception as exc:   # secondary line: never lose the headline over it
-            line["bimocq2d"] = {"error": repr(exc)}
+    # ---- the other BASELINE configs and the comparison legs (bounded: a few seconds each)
+    if not args.no_extras:
+        extras = {}
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
+        def leg(name, fn):
+            try:
+                extras[name] = fn()
+            except Exception as exc:   # noqa: BLE001 -- secondary lines: never lose the headline over them
+                extras[name] = {"error": repr(exc)}
+
+        if world == 1:
+            leg("general_h", lambda: short_run(torch, dist, world, rank, dev, args, kind, n, 0.2 if L == 1.0 else 1.0, steps=min(args.steps, 6)))
+            others = {}
+            for wname in ("plume128", "rings256"):
+                if wname != args.workload:
+                    wn, wkind, _ = WORKLOADS[wname]
+                    others[wname] = short_run(torch, dist, world, rank, dev, args, wkind, wn, 1.0)
+            extras["workloads"] = others
+            leg("reference_gpu", lambda: measure_reference_gpu(torch))
+            if not args.no_2d:
+                leg("bimocq2d", lambda: measure_2d(torch))
+        else:
+            # BASELINE configs[3]: the rings at 256^3, z-slab sharded over the same ranks (all ranks take part)
+            wn, wkind, _ = WORKLOADS["rings256"]
+            try:
+                r = short_run(torch, dist, world, rank, dev, args, wkind, wn, 1.0)
+            except Exception as exc:   # noqa: BLE001
+                r = {"error": repr(exc)}
+            extras["workloads"] = {"rings256": r}
+        if line is not None:
+            line.update(extras)
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on bounded samples
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        rate, sec = cpu_oracle_rate(args.ref_size, 2, 0)
+        rate, sec = cpu_oracle_rate(args.ref_size, 1, 0)
+        rate64, sec64 = cpu_oracle_rate(64, 2, 0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.ref_size}^3 plume, 2 steps ({sec:.1f} s/step): C restatement of the reference "
-                                          "CUDA kernels with OpenMP (the 3D reference has no CPU advection path)"}
-    if world > 1 and rank == 0 and getattr(solver, "stepper", None) is not None and solver.stepper.profile:
-        print("ZSLAB_PROFILE", {k: round(v, 4) for k, v in solver.stepper.prof.items()}, file=sys.stderr)
+                                "sample": f"{args.ref_size}^3 plume, 1 step ({sec:.1f} s): C restatement of the reference CUDA kernels "
+                                          "with OpenMP (the 3D reference has no CPU advection path)",
+                                "per_cell_scaling_check": {"64^3": {"value": rate64, "s_per_step": sec64},
+                                                           f"{args.ref_size}^3": {"value": rate, "s_per_step": sec}}}
     if line is not None:
         emit(line)
-    solver.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_reference_gpu(torch, n=256, steps=2):
+    """The kernel to beat: the reference's own CUDA kernels (oracle/_ref/libref3d.so =
+    GPU_kernel.cu compiled unmodified for sm_100a) driven through the reference's call sequence
+    (tests/helpers.DeviceStepper = BimocqSolver::advanceBimocq with MapperBase buffer semantics, device
+    resident) on the same B200 and the same 256^3 plume, next to this library's handle API."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    path = os.path.join(ROOT, "oracle", "_ref", "libref3d.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libref3d.so not built"}
+    from helpers import DeviceStepper
+    from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
+    L, h = 1.0, 1.0 / n
+    u, v, w, rho, T = [a.cpu().numpy() for a in make_scene("plume", n, L, torch, torch.device("cuda"))]
+    ref = DeviceStepper(n, n, n, h, 1.0, lib=C.CDLL(path))
+    ref.set_initial(u, v, w, rho, T)
+    ours = BimocqAdvection3D(n, n, n, h, 1.0)
+    ours.set_initial(u, v, w, rho, T)
+
+    def ref_step(frame):
+        ref.advect(frame, DT)
+        cur = [t.cpu().numpy() for t in ref.cur]
+        return cur
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        return a.elapsed_time(b)
+
+    t_ref_a = t_ref_b = t_our = 0.0
+    for frame in range(1 + steps):
+        ta = timed(lambda: ref.advect(frame, DT))
+        cur = [t.cpu().numpy() for t in ref.cur]
+        tb = timed(lambda: ref.accumulate(frame, DT, cur[:3], cur))
+        to = timed(lambda: (ours.advect(frame, DT), ours.accumulate(frame, DT)))
+        if frame > 0:
+            t_ref_a += ta; t_ref_b += tb; t_our += to
+    ours.close()
+    del ref
+    torch.cuda.empty_cache()
+    ref_ms = (t_ref_a + t_ref_b) / steps
+    return {"workload": f"smoke plume {n}^3, h = 1/{n}, {steps} steps after 1 warm-up, device resident",
+            "reference_kernels_ms_per_step": ref_ms, "reference_phase_a_ms": t_ref_a / steps, "reference_phase_b_ms": t_ref_b / steps,
+            "ours_ms_per_step": t_our / steps, "speedup": ref_ms / (t_our / steps),
+            "note": "reference side = GPU_kernel.cu unmodified (sm_100a) through MapperBaseGPU's call sequence incl. its "
+                    "device-to-device copies and the host-side max reductions it does; phase B's upload of the change fields "
+                    "from host arrays is inside its time (the reference forms them on the host, BimocqSolver.cpp:149-162)"}
 
 
 def measure_2d(torch, n=1024, steps=20, warm=5):
@@ -391,7 +534,46 @@ def measure_2d(torch, n=1024, steps=20, warm=5):
            "hbm_roofline_frac": (424 + 40 * nsub) * n * n / (ms * 1e-3) / 1e9 / measured_peak()[0],
            "note": "1 M cells x ~500 B = 0.5 GB/step: latency/launch bound, not HBM bound (BASELINE.md section 4)"}
     s.close()
+    try:
+        out["cpu_reference_2d"] = measure_2d_cpu_reference()
+    except Exception as exc:   # noqa: BLE001
+        out["cpu_reference_2d"] = {"error": repr(exc)}
     return out
+
+
+def measure_2d_cpu_reference(n=256, steps=100):
+    """BASELINE configs[0]: the reference's own 2D code (bimocq2D/BimocqSolver2D.cpp compiled unmodified into
+    oracle/_ref/libref2d.so) on the host cores: hot-path stages of advanceBIMOCQ (everything except forces and
+    projection) over 100 steps at 256x256; tbb::parallel_for is a static-chunk std::thread shim (oracle/shim)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref2d
+    if not ref2d.available():
+        return {"unavailable": "oracle/_ref/libref2d.so not built"}
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("BMQ_SHIM_THREADS", str(cores))
+    L = 1.0
+    ref = ref2d.Ref2D(n, n, L, 1.0)
+    h = ref.h
+    dt = 0.5 * h
+    xn = np.arange(n + 1, dtype=np.float64) / n
+    psi = 2.0 * L * (np.sin(np.pi * xn)[None, :] ** 2) * (np.sin(np.pi * xn)[:, None] ** 2) * L / np.pi
+    u = ((psi[1:, :] - psi[:-1, :]) / h).astype(np.float32)
+    v = (-(psi[:, 1:] - psi[:, :-1]) / h).astype(np.float32)
+    xc = (np.arange(n, dtype=np.float64) + 0.5) / n
+    rho = np.exp(-((xc[None, :] - 0.5) ** 2 + (xc[:, None] - 0.7) ** 2) / 0.12 ** 2).astype(np.float32)
+    T = np.exp(-((xc[None, :] - 0.4) ** 2 + (xc[:, None] - 0.3) ** 2) / 0.1 ** 2).astype(np.float32)
+    for mem, a in (("u", u), ("v", v), ("u_init", u), ("v_init", v), ("rho", rho), ("temperature", T), ("rho_init", rho), ("T_init", T)):
+        ref.field(mem)[...] = a
+    t0 = time.perf_counter()
+    for frame in range(steps):
+        ref.phase_a(dt, frame)
+        adv = [np.array(ref.field(m)) for m in ("u", "v", "rho", "temperature")]
+        ref.phase_b(dt, frame, adv[0], adv[1], adv[0], adv[1], adv[2], adv[3])
+    sec = time.perf_counter() - t0
+    ref.close()
+    return {"workload": f"BiMocq2D vortex-in-a-box {n}x{n}, {steps} steps, the reference's own C++ (hot-path stages)",
+            "cores": int(os.environ["BMQ_SHIM_THREADS"]), "kind": "reference", "s_total": sec, "ms_per_step": sec / steps * 1e3,
+            "cell_updates_per_s": n * n * steps / sec}
 
 
 def measure_e2e(solver, torch, n, args, frame):
@@ -478,12 +660,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--workload", default="plume512", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", type=int, default=0, help="override the workload's grid size (n^3)")
+    ap.add_argument("--domain-length", type=float, default=1.0, dest="domain_length",
+                    help="L: cell size h = L/n.  1.0 = power-of-two h (headline), 0.2 = the reference scene's cell size")
+    ap.add_argument("--no-extras", action="store_true", dest="no_extras",
+                    help="skip general_h / workloads / reference_gpu / bimocq2d (headline, e2e and cpu_baseline only)")
     ap.add_argument("--halo", type=int, default=None,
                     help="z-slab halo planes to allocate; default: the reach of the scalar mapper's 30-frame reinit cap "
                          "(zslab.default_halo); grows on demand")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="z-slab halo exchange: P2P copies or NCCL send/recv")
-    ap.add_argument("--ref-size", type=int, default=64, dest="ref_size")
+    ap.add_argument("--ref-size", type=int, default=128, dest="ref_size", help="grid of the CPU oracle sample (n^3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
