@@ -494,7 +494,7 @@ def measure_reference_gpu(torch, n=256, steps=2):
                     "from host arrays is inside its time (the reference forms them on the host, BimocqSolver.cpp:149-162)"}
 
 
-def measure_2d(torch, n=1024, steps=20, warm=5):
+def measure_2d(torch, n=1024, steps=20, warm=5, cpu_leg=True):
     """BASELINE configs[1]: BiMocq2D 1024x1024 on one B200 (device-resident bmq2d_* path), vortex-in-a-box
     flow with two scalar blobs; the caller stand-in between the phases is a device copy (zero forces)."""
     from gpufluidsimulation_b200.solver2d import BimocqAdvection2D
@@ -534,10 +534,11 @@ def measure_2d(torch, n=1024, steps=20, warm=5):
            "hbm_roofline_frac": (424 + 40 * nsub) * n * n / (ms * 1e-3) / 1e9 / measured_peak()[0],
            "note": "1 M cells x ~500 B = 0.5 GB/step: latency/launch bound, not HBM bound (BASELINE.md section 4)"}
     s.close()
-    try:
-        out["cpu_reference_2d"] = measure_2d_cpu_reference()
-    except Exception as exc:   # noqa: BLE001
-        out["cpu_reference_2d"] = {"error": repr(exc)}
+    if cpu_leg:
+        try:
+            out["cpu_reference_2d"] = measure_2d_cpu_reference()
+        except Exception as exc:   # noqa: BLE001
+            out["cpu_reference_2d"] = {"error": repr(exc)}
     return out
 
 
@@ -609,7 +610,8 @@ def measure_e2e(solver, torch, n, args, frame):
 def measure_e2e_slabs(solver, torch, dist, n, args, frame, world):
     """The same step through host buffers on N GPUs: every rank uploads / downloads the planes it owns
     over its own PCIe link (ZSlabAdvection3D.advect_host / accumulate_host), halos travel over NVLink
-    as in the device-resident step.  Time = max over ranks between two barriers."""
+    as in the device-resident step.  Time = max over ranks between two barriers.  Also times the SAME
+    transfers alone (all ranks at once, no kernels): the host-side bandwidth wall the e2e number sits on."""
     host = solver.alloc_host()
     for hb, nm in zip(host, ("U", "V", "W", "RHO", "T")):
         hb.copy_(solver.owned(nm))
@@ -618,22 +620,43 @@ def measure_e2e_slabs(solver, torch, dist, n, args, frame, world):
     counts = torch.tensor([float(sum(nbytes[:3]) * 2 + sum(nbytes)), float(sum(nbytes))], device="cuda")
     dist.all_reduce(counts)
     steps = max(2, min(args.steps, 4))
-    total = 0.0
-    for it in range(1 + steps):
+
+    def timed(fn):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        solver.advect_host(frame, DT, host)
-        solver.accumulate_host(frame, DT, host[:3], host)
+        fn()
         torch.cuda.synchronize()
         t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total = 0.0
+    for it in range(1 + steps):
+        def one():
+            solver.advect_host(frame, DT, host)
+            solver.accumulate_host(frame, DT, host[:3], host)
+        t = timed(one)
         frame += 1
         if it > 0:
-            total += float(t.item())
+            total += t
+    # the transfers of one step alone: 3 + 3 + 5 uploads and 5 downloads of the owned planes, all ranks at once
+    dev = [torch.empty_like(hb, device="cuda") for hb in host]
+
+    def copies():
+        for q in (0, 1, 2, 0, 1, 2, 0, 1, 2, 3, 4):
+            dev[q].copy_(host[q], non_blocking=True)
+        for q in range(5):
+            host[q].copy_(dev[q], non_blocking=True)
+    timed(copies)
+    copy_s = min(timed(copies) for _ in range(2))
+    moved = float(counts[0].item() + counts[1].item())
     return {"value": n ** 3 * steps / total, "unit": UNIT, "h2d_bytes_per_step": int(counts[0].item()),
             "d2h_bytes_per_step": int(counts[1].item()), "ms_per_step": total / steps * 1e3, "steps": steps,
-            "path": f"ZSlabAdvection3D.advect_host + accumulate_host on {world} ranks, pinned host buffers of the owned planes"}
+            "transfers_alone_ms_per_step": copy_s * 1e3, "transfers_alone_aggregate_gbs": moved / copy_s / 1e9,
+            "path": f"ZSlabAdvection3D.advect_host + accumulate_host on {world} ranks, pinned host buffers of the owned planes; "
+                    "transfers_alone = the same H2D/D2H copies of one step issued by all ranks at once with no kernels "
+                    "(the host-side bandwidth the e2e step cannot beat)"}
 
 
 _REAL_STDOUT = None

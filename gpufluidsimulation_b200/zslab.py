@@ -200,10 +200,11 @@ class PeerComm(DistComm):
     """Halo exchange by direct peer-to-peer copies over NVLink instead of NCCL send/recv.
 
     Every rank exports CUDA IPC handles of all its field allocations once; every other rank maps
-    them.  An exchange is then (1) a stream-ordered barrier -- a one-element NCCL all-reduce, so
-    every rank's producer kernel has finished, without blocking any host -- and (2) each rank
-    PULLING its halo planes straight out of the owners' planes with cudaMemcpyAsync on a
-    dedicated copy stream (measured: NCCL send/recv of these 10 MB blocks reaches < 100 GB/s on
+    them.  An exchange is then (1) a stream-ordered barrier -- a one-element NCCL all-reduce on the
+    COPY stream (which first waits for this rank's producer kernels), so every rank's producers have
+    finished, without blocking any host or the compute stream -- and (2) each rank
+    PULLING its halo planes straight out of the owners' planes with cudaMemcpyAsync on that
+    copy stream (measured: NCCL send/recv of these 10 MB blocks reaches < 100 GB/s on
     this box, a peer copy ~700 GB/s).  The copy stream is joined to the compute stream by events,
     so an exchange posted with exchange_async overlaps the kernels launched before wait().
 
@@ -292,12 +293,15 @@ class PeerComm(DistComm):
     def exchange_async(self, ranks, groups):
         torch = self.torch
         (r,) = ranks
-        # (1) barrier in stream order: all producers (on every rank) are complete afterwards
-        self.dist.all_reduce(self.flag)
-        # (2) pull on the copy stream, which first waits for the barrier on the compute stream
+        # Everything below runs on the copy stream, so the compute stream is never held up by the barrier:
+        # (1) the copy stream waits for this rank's producers (all work queued on the compute stream so far),
+        # (2) barrier in stream order -- a one-element all-reduce: afterwards every rank's producers are complete,
+        # (3) pull the halo planes out of their owners' memory.
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.copy_stream.wait_event(ev)
+        with torch.cuda.stream(self.copy_stream):
+            self.dist.all_reduce(self.flag)
         cs = C.c_void_p(self.copy_stream.cuda_stream)
         for names, width in groups:
             for name in names:

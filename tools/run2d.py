@@ -1,4 +1,4 @@
-"""Developer tool: a few 1024^2 BiMocq2D steps (for ncu launch lists)."""
+"""Developer tool for ncu launch lists: a few BiMocq2D steps at n x n (default 1024) through the handle API."""
 import os
 import sys
 
@@ -7,4 +7,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
-print(bench.measure_2d(torch, n=int(sys.argv[1]) if len(sys.argv) > 1 else 1024, steps=3, warm=2))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+print(bench.measure_2d(torch, n=n, steps=steps, warm=2, cpu_leg=False))
