@@ -49,10 +49,11 @@ __global__ void __launch_bounds__(256) k_verify_div(float h, float inv_h, unsign
 
 // true when div_h reproduces IEEE division by h for every float in [0, p_max] (the sequence is odd in p, so
 // negative positions are covered).  Checked once per (h, range) on the current device: ~1e9 quotients, a few ms.
-static bool division_verified(float h, float p_max)
+bool division_verified(float h, float p_max)
 {
     static std::mutex mu;
     static std::map<unsigned, std::pair<float, bool>> cache;    // bits of h -> (verified range, outcome)
+    if (!g_fast_division.load(std::memory_order_relaxed)) return false;      // testing knob: IEEE division everywhere
     unsigned key;
     memcpy(&key, &h, sizeof key);
     std::lock_guard<std::mutex> lock(mu);
@@ -81,7 +82,7 @@ Grid3 make_grid(int ni, int nj, int nk, float h)
         // positions stay inside the clamped domain plus one DMC reach; verify four times the domain
         int nmax = ni > nj ? ni : nj;
         nmax = nmax > nk ? nmax : nk;
-        if (!g_fast_division.load(std::memory_order_relaxed) || !division_verified(h, 4.0f * (float)(nmax + 8) * h)) g.inv_h = -g.inv_h;
+        if (!division_verified(h, 4.0f * (float)(nmax + 8) * h)) g.inv_h = -g.inv_h;
     }
     return g;
 }

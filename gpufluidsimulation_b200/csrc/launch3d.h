@@ -31,6 +31,8 @@ void set_pitch_specialisation(bool on);   // testing knob, see bmq_set_pitch_spe
 void set_gather_variant(int v);           // testing knob, see bmq_set_gather_variant
 void set_fast_division(bool on);          // testing knob, see bmq_set_fast_division
 bool division_is_fast(float h, int nmax);
+// div_h (device3d.cuh) == IEEE division by h for every float in {0} U [2^-100, p_max]?  Checked on the device, cached per h.
+bool division_verified(float h, float p_max);
 // z-marching gather kernels (march_*.cu); same contracts as launch_advect / _error / _cumulate / _apply_clamp
 // with is_point == false
 cudaError_t launch_advect_march(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, float *const *out,

@@ -15,6 +15,7 @@
 // Layout: row-major a[i + ni*j] (array2.h:93-103).  Cell centre (i+1/2, j+1/2) h, u at
 // (i, j+1/2) h, v at (i+1/2, j) h.
 #include "common.h"
+#include "launch3d.h"
 
 #include <cmath>
 #include <cstring>
@@ -26,6 +27,9 @@ namespace {
 struct G2 {
     int ni, nj;
     float h;
+    float inv_h;   // RN(1/h)
+    int div_mode;  // how pos / h is evaluated: 0 IEEE division, 1 exact multiplication (h a power of two), 2 the
+                   // three-instruction sequence of device3d.cuh:div_h, verified for this h (kernels3d.cu)
 };
 
 #define FM(a, b) __fmul_rn((a), (b))
@@ -37,6 +41,19 @@ struct V2 {
     float x, y;
 };
 
+// pos / h as the reference's CPU code computes it (a correctly rounded float division), without the ~10
+// instruction IEEE division sequence where it can be avoided bit for bit
+__device__ __forceinline__ float div_cell(float p, const G2 &g)
+{
+    if (g.div_mode == 1) return FM(p, g.inv_h);
+    if (g.div_mode == 2 && (fabsf(p) >= 7.888609052e-31f || p == 0.f)) {
+        const float q0 = FM(p, g.inv_h);
+        const float r = __fmaf_rn(-g.h, q0, p);
+        return __fmaf_rn(r, g.inv_h, q0);
+    }
+    return FD(p, g.h);
+}
+
 // lerp / bilerp, BimocqSolver2D.cpp:71-79
 __device__ __forceinline__ float lerp2(float v0, float v1, float c) { return FA(FM(FS(1.0f, c), v0), FM(c, v1)); }
 __device__ __forceinline__ float bilerp2(float v00, float v01, float v10, float v11, float cx, float cy)
@@ -45,9 +62,9 @@ __device__ __forceinline__ float bilerp2(float v00, float v01, float v10, float 
 }
 
 // sampleField, :2328-2334 with Array2::boundedAt (array2.h:273-284)
-__device__ __forceinline__ float sample_field(const float *__restrict__ f, int fni, int fnj, float h, float px, float py)
+__device__ __forceinline__ float sample_field(const float *__restrict__ f, int fni, int fnj, const G2 &g, float px, float py)
 {
-    const float qx = FD(px, h), qy = FD(py, h);
+    const float qx = div_cell(px, g), qy = div_cell(py, g);
     const int i = (int)floorf(qx), j = (int)floorf(qy);
     const int i0 = min(max(i, 0), fni - 1), i1 = min(max(i + 1, 0), fni - 1);
     const int j0 = min(max(j, 0), fnj - 1), j1 = min(max(j + 1, 0), fnj - 1);
@@ -62,7 +79,7 @@ __device__ __forceinline__ V2 get_velocity(const G2 &g, const float *__restrict_
     V2 r;
     {
         const float ux = FS(pos.x, 0.0f), uy = FS(pos.y, hh);
-        const float qx = FD(ux, g.h), qy = FD(uy, g.h);
+        const float qx = div_cell(ux, g), qy = div_cell(uy, g);
         const int i = (int)floorf(qx), j = (int)floorf(qy);
         if (!(i >= 0 && i <= g.ni - 1 && j >= 0 && j <= g.nj - 2)) r.x = 0.f;
         else {
@@ -73,7 +90,7 @@ __device__ __forceinline__ V2 get_velocity(const G2 &g, const float *__restrict_
     }
     {
         const float vx = FS(pos.x, hh), vy = FS(pos.y, 0.0f);
-        const float qx = FD(vx, g.h), qy = FD(vy, g.h);
+        const float qx = div_cell(vx, g), qy = div_cell(vy, g);
         const int i = (int)floorf(qx), j = (int)floorf(qy);
         if (!(i >= 0 && i <= g.ni - 2 && j >= 0 && j <= g.nj - 1)) r.y = 0.f;
         else {
@@ -189,7 +206,7 @@ __device__ __forceinline__ V2 map_through(const G2 &g, const float *mx, const fl
 {
     const float hh = FM(g.h, 0.5f);
     const float sx = FS(pos.x, hh), sy = FS(pos.y, hh);
-    V2 r = {sample_field(mx, g.ni, g.nj, g.h, sx, sy), sample_field(my, g.ni, g.nj, g.h, sx, sy)};
+    V2 r = {sample_field(mx, g.ni, g.nj, g, sx, sy), sample_field(my, g.ni, g.nj, g, sx, sy)};
     clamp_pos(g, r);
     return r;
 }
@@ -243,8 +260,8 @@ k2_backward(G2 g, const float *u, const float *v, const float *bx, const float *
     V2 b = solve_ode_dmc(g, u, v, substep, pos);
     clamp_pos(g, b);
     const float sx = FS(b.x, hh), sy = FS(b.y, hh);
-    ox[idx] = sample_field(bx, g.ni, g.nj, g.h, sx, sy);
-    oy[idx] = sample_field(by, g.ni, g.nj, g.h, sx, sy);
+    ox[idx] = sample_field(bx, g.ni, g.nj, g, sx, sy);
+    oy[idx] = sample_field(by, g.ni, g.nj, g, sx, sy);
 }
 
 // semiLagAdvect, :110-123 (same two-pass scheme as k2_forward)
@@ -258,7 +275,7 @@ k2_semilag(G2 g, const float *u, const float *v, const float *src, float *dst, i
         IJ(fni, fnj)
         V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)}, b;
         if (!solve_ode_quick(g, u, v, -dt, pos, b)) { defer(wl, idx); return; }
-        dst[idx] = sample_field(src, fni, fnj, g.h, FS(b.x, ox), FS(b.y, oy));
+        dst[idx] = sample_field(src, fni, fnj, g, FS(b.x, ox), FS(b.y, oy));
     } else {
         const int n = *wl.count;
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -266,7 +283,7 @@ k2_semilag(G2 g, const float *u, const float *v, const float *src, float *dst, i
             const int i = idx % fni, j = idx / fni;
             V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)};
             V2 b = solve_ode(g, u, v, -dt, pos);
-            dst[idx] = sample_field(src, fni, fnj, g.h, FS(b.x, ox), FS(b.y, oy));
+            dst[idx] = sample_field(src, fni, fnj, g, FS(b.x, ox), FS(b.y, oy));
         }
     }
 }
@@ -294,11 +311,11 @@ __global__ void __launch_bounds__(256) k2_advect(G2 g, AdvectArgs a)
         const V2 p1 = map_through(g, a.bx, a.by, pos);
         const V2 p2 = map_through(g, a.bxp, a.byp, p1);
         const float w = quad_w(k);
-        const float s_orig = sample_field(a.f_orig, a.fni, a.fnj, g.h, FS(p2.x, ox), FS(p2.y, oy));
-        const float s_d1 = sample_field(a.d, a.fni, a.fnj, g.h, FS(p1.x, ox), FS(p1.y, oy));
-        const float s_dp = sample_field(a.d_prev, a.fni, a.fnj, g.h, FS(p2.x, ox), FS(p2.y, oy));
+        const float s_orig = sample_field(a.f_orig, a.fni, a.fnj, g, FS(p2.x, ox), FS(p2.y, oy));
+        const float s_d1 = sample_field(a.d, a.fni, a.fnj, g, FS(p1.x, ox), FS(p1.y, oy));
+        const float s_dp = sample_field(a.d_prev, a.fni, a.fnj, g, FS(p2.x, ox), FS(p2.y, oy));
         acc = FA(acc, FM(FM(omb, w), FA(FA(s_orig, s_d1), s_dp)));
-        const float s_init = sample_field(a.f_init, a.fni, a.fnj, g.h, FS(p1.x, ox), FS(p1.y, oy));
+        const float s_init = sample_field(a.f_init, a.fni, a.fnj, g, FS(p1.x, ox), FS(p1.y, oy));
         acc = FA(acc, FM(FM(a.blend, w), FA(s_init, s_d1)));
     }
     a.out[idx] = acc;
@@ -325,7 +342,7 @@ __global__ void __launch_bounds__(256) k2_correct_error(G2 g, CorrectArgs a)
 #pragma unroll 1
         for (int k = 0; k < 5; ++k) {
             const V2 p1 = map_through(g, a.mx, a.my, quad_pos(g, i, j, a.offx, a.offy, k));
-            t = FA(t, FM(quad_w(k), FS(sample_field(a.src, a.fni, a.fnj, g.h, FS(p1.x, ox), FS(p1.y, oy)), dv)));
+            t = FA(t, FM(quad_w(k), FS(sample_field(a.src, a.fni, a.fnj, g, FS(p1.x, ox), FS(p1.y, oy)), dv)));
         }
     }
     a.out[idx] = FM(FS(t, __ldg(a.f_init + idx)), 0.5f);
@@ -341,7 +358,7 @@ __global__ void __launch_bounds__(256) k2_correct_apply(G2 g, CorrectArgs a)
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
         const V2 p1 = map_through(g, a.mx, a.my, quad_pos(g, i, j, a.offx, a.offy, k));
-        f = FS(f, FM(quad_w(k), sample_field(a.src, a.fni, a.fnj, g.h, FS(p1.x, ox), FS(p1.y, oy))));
+        f = FS(f, FM(quad_w(k), sample_field(a.src, a.fni, a.fnj, g, FS(p1.x, ox), FS(p1.y, oy))));
     }
     a.out[idx] = f;
 }
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(256) k2_accumulate(G2 g, AccumArgs a)
     for (int c = 0; c < a.nch; ++c) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const float s = sample_field(a.change[c], a.fni, a.fnj, g.h, FS(p[k].x, ox), FS(p[k].y, oy));
+            const float s = sample_field(a.change[c], a.fni, a.fnj, g, FS(p[k].x, ox), FS(p[k].y, oy));
             d = a.scalar_form ? FA(d, FM(quad_w(k), s)) : FA(d, FM(FM(quad_w(k), a.coeff[c]), s));
         }
     }
@@ -435,13 +452,13 @@ k2_distortion(G2 g, const float *bx, const float *by, const float *fx, const flo
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             const float f0x = __ldg(F[m][0] + idx), f0y = __ldg(F[m][1] + idx);
-            float qx = sample_field(B[m][0], g.ni, g.nj, g.h, FS(f0x, hh), FS(f0y, hh));
-            float qy = sample_field(B[m][1], g.ni, g.nj, g.h, FS(f0x, hh), FS(f0y, hh));
+            float qx = sample_field(B[m][0], g.ni, g.nj, g, FS(f0x, hh), FS(f0y, hh));
+            float qy = sample_field(B[m][1], g.ni, g.nj, g, FS(f0x, hh), FS(f0y, hh));
             float ex = FS(qx, ipx), ey = FS(qy, ipy);
             float dd = sqrtf(FA(FM(ex, ex), FM(ey, ey)));
             const float b0x = __ldg(B[m][0] + idx), b0y = __ldg(B[m][1] + idx);
-            qx = sample_field(F[m][0], g.ni, g.nj, g.h, FS(b0x, hh), FS(b0y, hh));
-            qy = sample_field(F[m][1], g.ni, g.nj, g.h, FS(b0x, hh), FS(b0y, hh));
+            qx = sample_field(F[m][0], g.ni, g.nj, g, FS(b0x, hh), FS(b0y, hh));
+            qy = sample_field(F[m][1], g.ni, g.nj, g, FS(b0x, hh), FS(b0y, hh));
             ex = FS(qx, ipx); ey = FS(qy, ipy);
             dd = fmaxf(dd, sqrtf(FA(FM(ex, ex), FM(ey, ey))));
             d[m] = dd;
@@ -594,7 +611,7 @@ int forward_quick(bmq2d_solver *s, float dt, int fx, int fy, int w)
 int forward_slow(bmq2d_solver *s, float dt, int fx, int fy, int w)
 {
     BMQ_CK(cudaStreamWaitEvent(s->side[w], s->ev_quick, 0));
-    k2_forward<true><<<148, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, worklist(s, w));
+    k2_forward<true><<<148 * 4, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, worklist(s, w));
     L2D(s);
     BMQ_CK(cudaGetLastError());
     BMQ_CK(cudaEventRecord(s->ev_side[w], s->side[w]));
@@ -616,7 +633,7 @@ int semilag_slow(bmq2d_solver *s, int src, int dst, float dt, int w)
 {
     FieldGeom q = geom(s, kind_of(src));
     BMQ_CK(cudaStreamWaitEvent(s->side[w], s->ev_quick, 0));
-    k2_semilag<true><<<148, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst], q.fni, q.fnj,
+    k2_semilag<true><<<148 * 4, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst], q.fni, q.fnj,
                                                q.offx, q.offy, dt, worklist(s, w));
     L2D(s);
     BMQ_CK(cudaGetLastError());
@@ -754,7 +771,13 @@ int bmq2d_create(int ni, int nj, float h, float blend_coeff, bmq2d_solver **out)
     bmq2d_solver *s = new (std::nothrow) bmq2d_solver();
     if (!s) return bmq::set_error(BMQ_ERR_ARG, "bmq2d_create: out of host memory");
     s->ni = ni; s->nj = nj; s->h = h; s->blend = blend_coeff;
-    s->g = G2{ni, nj, h};
+    s->g = G2{ni, nj, h, 1.0f / h, 0};
+    {
+        int e;
+        const int nmax = ni > nj ? ni : nj;
+        if (frexpf(h, &e) == 0.5f) s->g.div_mode = 1;                                                  // power of two: exact
+        else if (bmq::division_verified(h, 4.0f * (float)(nmax + 8) * h)) s->g.div_mode = 2;          // checked exhaustively
+    }
     memset(&s->stats, 0, sizeof s->stats);
     int st = BMQ_OK;
     for (int id = 0; id < BMQ2_F_COUNT && st == BMQ_OK; ++id) {
