@@ -3,6 +3,7 @@
 // Same prototypes, same buffer/aliasing contract, legacy default stream, void returns with the
 // error latched for bmq_last_error().
 #include "common.h"
+#include <mutex>
 #include "launch3d.h"
 
 using namespace bmq;
@@ -190,8 +191,19 @@ int bmq_max_abs3(const float *u, long long nu, const float *v, long long nv, con
 {
     if (!host_out || nu < 0 || nv < 0 || nw < 0) return set_error(BMQ_ERR_ARG, "bmq_max_abs3: bad argument");
     if (!require_device()) return BMQ_ERR_NODEVICE;
-    static float *d_red = nullptr;   // 4-byte device scalar, allocated once per process
-    if (!d_red) BMQ_CK(cudaMalloc(&d_red, sizeof(float)));
+    // 4-byte device scalar per device, allocated once; the legacy entry points are single-threaded per device
+    // (they share the legacy default stream and, like the reference's gpuMapper, caller-owned scratch)
+    static std::mutex mu;
+    static float *scratch[64] = {};
+    int dev = 0;
+    BMQ_CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(BMQ_ERR_ARG, "bmq_max_abs3: device ordinal %d out of range", dev);
+    float *d_red = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!scratch[dev]) BMQ_CK(cudaMalloc(&scratch[dev], sizeof(float)));
+        d_red = scratch[dev];
+    }
     BMQ_CK(cudaMemsetAsync(d_red, 0, sizeof(float), kLegacy));
     BMQ_CK(launch_maxabs3(kLegacy, u, (size_t)nu, v, (size_t)nv, w, (size_t)nw, d_red));
     BMQ_CK(cudaMemcpy(host_out, d_red, sizeof(float), cudaMemcpyDeviceToHost));

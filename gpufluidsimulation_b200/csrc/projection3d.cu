@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "common.h"
+#include <mutex>
 
 namespace bmq {
 void count_launches(unsigned n);   // kernels3d.cu
@@ -591,8 +592,18 @@ void gpu_multi_grid_conjugate_gradient(float *u, float *v, float *w, double *div
         bmq::set_error(BMQ_ERR_ARG, "gpu_multi_grid_conjugate_gradient: bad level table");
         return;
     }
-    static double *scratch = nullptr;   // 257 doubles of device scratch, allocated once per process
-    if (!scratch) BMQ_CKV(cudaMalloc(&scratch, 257 * sizeof(double)));
+    // 257 doubles of device scratch per device, allocated once (legacy entry points: one host thread per device)
+    static std::mutex mu;
+    static double *per_device[64] = {};
+    int dev = 0;
+    BMQ_CKV(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { bmq::set_error(BMQ_ERR_ARG, "gpu_multi_grid_conjugate_gradient: device ordinal out of range"); return; }
+    double *scratch = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!per_device[dev]) BMQ_CKV(cudaMalloc(&per_device[dev], 257 * sizeof(double)));
+        scratch = per_device[dev];
+    }
     Mg mg{0, scratch, reinterpret_cast<unsigned long long *>(scratch)};
     mg.solve(u, v, w, div, p, dir, residual, temp0, temp1, tempResult, levels, levelNum, iter, halfrdx);
 }

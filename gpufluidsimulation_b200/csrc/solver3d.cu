@@ -826,9 +826,26 @@ static int upload_async(bmq3d_solver *s, Field &fd, const float *host, cudaEvent
 // only u,v,w are uploaded (phase A never reads the current density / temperature: they are pure
 // outputs of MapperBase::advectField, Mapping.cpp:208-236); u,v,w travel back while the scalar
 // stages run.
+// Error exits of the *_host calls must not leave asynchronous copies touching the caller's buffers in flight.
+struct HostCallGuard {
+    bmq3d_solver *s;
+    ~HostCallGuard()
+    {
+        if (s->s_h2d) cudaStreamSynchronize(s->s_h2d);
+        if (s->s_d2h) cudaStreamSynchronize(s->s_d2h);
+        cudaStreamSynchronize(s->stream);
+    }
+};
+
+static int advect_host_impl(bmq3d_solver *s, int framenum, float dt, float *u, float *v, float *w, float *rho, float *T);
 int bmq3d_advect_host(bmq3d_solver *s, int framenum, float dt, float *u, float *v, float *w, float *rho, float *T)
 {
     NEED(s);
+    HostCallGuard guard{s};      // runs after the body, on every path
+    return advect_host_impl(s, framenum, dt, u, v, w, rho, T);
+}
+static int advect_host_impl(bmq3d_solver *s, int framenum, float dt, float *u, float *v, float *w, float *rho, float *T)
+{
     if (!(dt > 0.f)) return set_error(BMQ_ERR_ARG, "bmq3d_advect_host: dt must be positive");
     float *host[5] = {u, v, w, rho, T};
     for (int c = 0; c < 5; ++c)
@@ -879,11 +896,21 @@ int bmq3d_advect_host(bmq3d_solver *s, int framenum, float dt, float *u, float *
     return BMQ_OK;
 }
 
+static int accumulate_host_impl(bmq3d_solver *s, int framenum, float dt, const float *u_forced, const float *v_forced,
+                                const float *w_forced, const float *u_final, const float *v_final, const float *w_final,
+                                const float *rho_final, const float *T_final);
 int bmq3d_accumulate_host(bmq3d_solver *s, int framenum, float dt, const float *u_forced, const float *v_forced,
                           const float *w_forced, const float *u_final, const float *v_final, const float *w_final,
                           const float *rho_final, const float *T_final)
 {
     NEED(s);
+    HostCallGuard guard{s};
+    return accumulate_host_impl(s, framenum, dt, u_forced, v_forced, w_forced, u_final, v_final, w_final, rho_final, T_final);
+}
+static int accumulate_host_impl(bmq3d_solver *s, int framenum, float dt, const float *u_forced, const float *v_forced,
+                                const float *w_forced, const float *u_final, const float *v_final, const float *w_final,
+                                const float *rho_final, const float *T_final)
+{
     const float *forced[3] = {u_forced, v_forced, w_forced};
     const float *fin[5] = {u_final, v_final, w_final, rho_final, T_final};
     for (int c = 0; c < 5; ++c)

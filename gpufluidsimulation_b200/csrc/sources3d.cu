@@ -60,16 +60,19 @@ k_emit_field(float *rho, float *T, float h, int ni, int nj, int nk, float cx, fl
 
 // add_buoyancy_kernel, GPU_kernel.cu:804-823: v(i,j,k) += 0.5 dt (beta (T_j + T_{j-1}) - alpha (rho_j + rho_{j-1})).
 // The reference indexes density/temperature with the v-face index (nj+1 rows per plane), i.e. with
-// the v-field's row pitch; that addressing is reproduced (it is what the reference computes).
+// the v-field's row pitch; that addressing is reproduced (it is what the reference computes).  Through it
+// the last ni*nk face indices point past the end of the cell-centred arrays (the reference reads whatever
+// lies behind them); here such reads return 0 (n_scalar = number of floats density / temperature hold).
 __global__ void __launch_bounds__(128)
 k_add_buoyancy(float *field, const float *__restrict__ density, const float *__restrict__ temperature, int ni, int nj,
-               int nk, float alpha, float beta, float dt)
+               int nk, float alpha, float beta, float dt, long long n_scalar)
 {
     SRC_IJK(ni, nj, nk)
     if (!(j > 0)) return;
     const int index1 = index - ni;
-    const float d0 = density[index], T0 = temperature[index];
-    const float d1 = density[index1], T1 = temperature[index1];
+    const bool in0 = index < n_scalar, in1 = index1 < n_scalar;
+    const float d0 = in0 ? density[index] : 0.f, T0 = in0 ? temperature[index] : 0.f;
+    const float d1 = in1 ? density[index1] : 0.f, T1 = in1 ? temperature[index1] : 0.f;
     const float f = 0.5 * dt * (beta * (T0 + T1) - alpha * (d0 + d1));   // the reference's expression, same contraction
     field[index] += f;
 }
@@ -77,13 +80,16 @@ k_add_buoyancy(float *field, const float *__restrict__ density, const float *__r
 // the same with four cells per thread (128-bit accesses; needs ni % 4 == 0 and 16-byte aligned bases)
 __global__ void __launch_bounds__(128)
 k_add_buoyancy4(float *field, const float *__restrict__ density, const float *__restrict__ temperature, int ni, int nj,
-                int nk, float alpha, float beta, float dt)
+                int nk, float alpha, float beta, float dt, long long n_scalar)
 {
     const int i4 = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i4 * 4 >= ni || j >= nj || k >= nk || !(j > 0)) return;
     const size_t index = (size_t)i4 * 4 + (size_t)ni * (j + (size_t)nj * k), index1 = index - ni;
-    const float4 d0 = *reinterpret_cast<const float4 *>(density + index), T0 = *reinterpret_cast<const float4 *>(temperature + index);
-    const float4 d1 = *reinterpret_cast<const float4 *>(density + index1), T1 = *reinterpret_cast<const float4 *>(temperature + index1);
+    // n_scalar and both indices are multiples of 4 (ni % 4 == 0): a quad is wholly inside or wholly outside
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool in0 = (long long)index < n_scalar, in1 = (long long)index1 < n_scalar;
+    const float4 d0 = in0 ? *reinterpret_cast<const float4 *>(density + index) : zero, T0 = in0 ? *reinterpret_cast<const float4 *>(temperature + index) : zero;
+    const float4 d1 = in1 ? *reinterpret_cast<const float4 *>(density + index1) : zero, T1 = in1 ? *reinterpret_cast<const float4 *>(temperature + index1) : zero;
     float4 f = *reinterpret_cast<float4 *>(field + index);
     // the reference's expression per lane, same contraction
     const float ix = 0.5 * dt * (beta * (T0.x + T1.x) - alpha * (d0.x + d1.x));
@@ -267,8 +273,9 @@ void gpu_add_buoyancy(float *field, float *density, float *temperature, int ni, 
 {
     if (!bmq::require_device()) return;
     const bool vec = ni % 4 == 0 && ((reinterpret_cast<uintptr_t>(field) | reinterpret_cast<uintptr_t>(density) | reinterpret_cast<uintptr_t>(temperature)) & 15) == 0;
-    if (vec) k_add_buoyancy4<<<sgrd(ni / 4, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt);
-    else k_add_buoyancy<<<sgrd(ni, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt);
+    const long long n_scalar = (long long)ni * nj * nk;
+    if (vec) k_add_buoyancy4<<<sgrd(ni / 4, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt, n_scalar);
+    else k_add_buoyancy<<<sgrd(ni, nj + 1, nk), sblk()>>>(field, density, temperature, ni, nj + 1, nk, alpha, beta, dt, n_scalar);
     BMQ_CKV(cudaGetLastError());
 }
 

@@ -11,7 +11,9 @@
  *     against this library unchanged.  Each prototype cites the reference declaration it
  *     replaces.  All pointers are DEVICE pointers to dense x-fastest float arrays
  *     (idx = i + nx*j + nx*ny*k) of the sizes the reference uses; they run on the legacy
- *     default stream, return void, and latch errors for bmq_last_error().
+ *     default stream, return void, and latch errors for bmq_last_error().  Like the reference's
+ *     gpuMapper they are meant for ONE host thread per device (shared default stream, per-device
+ *     scratch); the handle APIs below are safe to use from different threads on different handles.
  *
  *  2. HANDLE API (bmq3d_*, bmq2d_*, bmq_mgpcg_*).  Device-resident solver state with the fused kernels and the
  *     reinitialisation scheduler of BimocqSolver::advanceBimocq (bimocq3D/BimocqSolver.cpp:88-230)
@@ -135,7 +137,10 @@ void gpu_add_field(float *out, float *field1, float *field2, float coeff, int nu
 void gpu_emit_smoke(float *u, float *v, float *w, float *rho, float *T, float h, int ni, int nj, int nk,
                     float centerX, float centerY, float centerZ, float radius, float density,
                     float temperature, float emiter);
-/* replaces GPU_Advection.h:92-93 (def. GPU_kernel.cu:825-832) */
+/* replaces GPU_Advection.h:92-93 (def. GPU_kernel.cu:825-832).  `field` is the v-face array (ni x (nj+1) x nk),
+ * density / temperature are cell-centred (ni x nj x nk) but -- as in the reference -- are indexed with the
+ * v-face index, so the last ni*nk face indices point past their end: the reference reads whatever memory
+ * follows, this library reads 0 there.  In-range arithmetic is the reference's, bit for bit. */
 void gpu_add_buoyancy(float *field, float *density, float *temperature, int ni, int nj, int nk,
                       float alpha, float beta, float dt);
 /* replaces GPU_Advection.h:95 (def. GPU_kernel.cu:855-876): `iter` Jacobi sweeps between the two
