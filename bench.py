@@ -692,7 +692,8 @@ def main():
     ap.add_argument("--halo", type=int, default=None,
                     help="z-slab halo planes to allocate; default: the reach of the scalar mapper's 30-frame reinit cap "
                          "(zslab.default_halo); grows on demand")
-    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="z-slab halo exchange: P2P copies or NCCL send/recv")
+    ap.add_argument("--transport", default="native", choices=["native", "peer", "nccl"],
+                    help="z-slab driver: the library's own (bmq3d_mg_*, peer copies), the Python stepper with peer copies, or with NCCL send/recv")
     ap.add_argument("--ref-size", type=int, default=128, dest="ref_size", help="grid of the CPU oracle sample (n^3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")

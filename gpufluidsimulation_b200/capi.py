@@ -84,6 +84,18 @@ FIELD2_NAMES = [
 FIELD2 = {n: i for i, n in enumerate(FIELD2_NAMES)}
 
 
+class MgStats(C.Structure):
+    _fields_ = [("halo_allocated", _I), ("halo_needed", _I), ("halo_vel", _I), ("halo_scalar", _I), ("halo_grown", _I),
+                ("exchanges", C.c_longlong), ("bytes_exchanged", C.c_longlong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+ALLREDUCE_MAX_FN = C.CFUNCTYPE(_I, C.POINTER(_f), _I, C.c_void_p)
+STREAM_BARRIER_FN = C.CFUNCTYPE(_I, C.c_void_p, C.c_void_p)
+
+
 class Stats2D(C.Structure):
     _fields_ = [("cfl", _f), ("max_vel_pre", _f), ("n_substeps", _I), ("max_vel", _f), ("vel_condition", _f),
                 ("scalar_condition", _f), ("vel_remap", _I), ("scalar_remap", _I), ("last_remesh", _I),
@@ -177,6 +189,18 @@ _PROTOS = {
     "bmq2d_advect_host": (_I, [_H, _I, _f] + [C.c_void_p] * 4),
     "bmq2d_accumulate_host": (_I, [_H, _I, _f] + [C.c_void_p] * 6),
     "bmq2d_kernel_launch_count": (C.c_ulonglong, [_H]),
+    "bmq3d_mg_create": (_I, [_I, _I, _I, _f, _f, _I, _I, _I, C.POINTER(_H)]),
+    "bmq3d_mg_destroy": (_I, [_H]),
+    "bmq3d_mg_solver": (_I, [_H, C.POINTER(_H)]),
+    "bmq3d_mg_set_collectives": (_I, [_H, ALLREDUCE_MAX_FN, STREAM_BARRIER_FN, C.c_void_p]),
+    "bmq3d_mg_export_size": (_I, [_H, C.POINTER(C.c_size_t)]),
+    "bmq3d_mg_export": (_I, [_H, C.c_void_p]),
+    "bmq3d_mg_connect": (_I, [_H, C.c_void_p]),
+    "bmq3d_mg_disconnect": (_I, [_H]),
+    "bmq3d_mg_grow_halo": (_I, [_H, _I]),
+    "bmq3d_mg_advect": (_I, [_H, _I, _f]),
+    "bmq3d_mg_accumulate": (_I, [_H, _I, _f]),
+    "bmq3d_mg_get_stats": (_I, [_H, C.POINTER(MgStats)]),
     "bmq3d_stage_maxvel": (_I, [_H, C.POINTER(_f)]),
     "bmq3d_stage_set_cfl": (_I, [_H, _I, _f]),
     "bmq3d_stage_dmc_substep": (_I, [_H, _f]),

@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <unistd.h>
 #include <new>
 #include <utility>
 #include <vector>
@@ -27,6 +28,7 @@ namespace {
 enum { N_SCRATCH = 10, SCRATCH_BASE = 64, N_TMPMAP = 6 };
 
 struct Field {
+    int alloc_id = -1;        // identity of the allocation: stays with the buffer when fields rotate (z-slab peers index by it)
     float *alloc = nullptr;   // first stored plane
     int nx = 0, ny = 0, nz = 0;   // full (global) dims of the field
     int p0 = 0, p1 = 0;       // stored global planes [p0, p1)
@@ -41,6 +43,7 @@ struct bmq3d_solver {
     int ni, nj, nk;
     float h, blend;
     int k0, k1, halo;          // owned planes [k0,k1), halo width
+    int n_allocs = 0;          // allocation ids handed out so far (Field::alloc_id)
     cudaStream_t stream = 0;
     Grid3 g;
     Field f[BMQ_F_COUNT];
@@ -95,6 +98,7 @@ int alloc_field(bmq3d_solver *s, Field &fd, Stag st)
     fd.p0 = s->k0 - s->halo > 0 ? s->k0 - s->halo : 0;
     fd.p1 = s->k1 + s->halo + 1 < fd.nz ? s->k1 + s->halo + 1 : fd.nz;
     const size_t n = fd.stored_elems() + fd.plane() + fd.nx + 2;   // zero padding, see file header
+    if (fd.alloc_id < 0) fd.alloc_id = s->n_allocs++;
     BMQ_CK(cudaMalloc(&fd.alloc, n * sizeof(float)));
     BMQ_CK(cudaMemsetAsync(fd.alloc, 0, n * sizeof(float), s->stream));
     return BMQ_OK;
@@ -961,6 +965,388 @@ static int accumulate_host_impl(bmq3d_solver *s, int framenum, float dt, const f
     s->stats.vel_reinit_count = s->vel_reinit_count;
     s->stats.scalar_reinit_count = s->scalar_reinit_count;
     BMQ_CK(cudaStreamSynchronize(s->stream));
+    return BMQ_OK;
+}
+
+
+}  // extern "C"
+
+// ==================================================================================================
+// bmq3d_mg_*: the z-slab decomposition as a C API.  One bmq3d_mg per rank / GPU /
+// process; it owns the rank's slab handle, maps every other rank's field allocations (CUDA IPC, or raw
+// pointers when several ranks live in one process) and runs the advection phases with the halo
+// exchanges of gpufluidsimulation_b200/zslab.py:ZSlabStepper -- same schedule, same widths -- as
+// stream-ordered peer copies over NVLink.  What it cannot do itself, because the host program owns the
+// communicator, comes in as two callbacks: a max all-reduce of a few floats and a barrier ordered in a
+// CUDA stream.
+// ==================================================================================================
+namespace {
+
+enum { MG_NARROW = 5, MG_EVENTS = 32 };
+
+struct MgGroup { const int *ids; int n; int width; };
+
+struct MgBlobHeader { long long pid; int n_allocs; int halo; int rank; int pad; };
+struct MgBlobEntry { unsigned char ipc[64]; void *raw; };
+
+int mg_slab_k0(int nk, int world, int r) { const int base = nk / world, rem = nk % world; return r * base + (r < rem ? r : rem); }
+
+}  // namespace
+
+struct bmq3d_mg {
+    bmq3d_solver *s = nullptr;
+    int rank = 0, world = 1;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev[MG_EVENTS] = {};
+    int ev_next = 0;
+    std::vector<std::vector<void *>> peer;      // [rank][alloc_id]: base of that rank's allocation, mapped here
+    std::vector<char> peer_is_ipc;              // [rank]: mapped with cudaIpcOpenMemHandle (must be closed)
+    bmq_allreduce_max_fn allreduce = nullptr;
+    bmq_stream_barrier_fn barrier = nullptr;
+    void *ctx = nullptr;
+    float disp[2] = {0.f, 0.f}, disp_prev[2] = {0.f, 0.f};
+    int reinit_count[2] = {0, 0};
+    int wv = 3, ws = 3;
+    bmq3d_mg_stats stats;
+};
+
+namespace {
+
+cudaEvent_t mg_event(bmq3d_mg *m) { cudaEvent_t e = m->ev[m->ev_next]; m->ev_next = (m->ev_next + 1) % MG_EVENTS; return e; }
+
+// global planes [a, b) of a field that rank r owns (w faces: the top face belongs to the last rank)
+void mg_owned(const bmq3d_mg *m, int dz, int r, int &a, int &b)
+{
+    const int nk = m->s->nk;
+    a = mg_slab_k0(nk, m->world, r);
+    b = mg_slab_k0(nk, m->world, r + 1) + ((dz && r == m->world - 1) ? 1 : 0);
+}
+
+// Posts one exchange on the copy stream: wait for this rank's producers, barrier, pull every halo segment
+// out of its owner's memory.  Returns the event the consumers wait for.
+int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, cudaEvent_t *done)
+{
+    bmq3d_solver *s = m->s;
+    cudaEvent_t produced = mg_event(m);
+    BMQ_CK(cudaEventRecord(produced, s->stream));
+    BMQ_CK(cudaStreamWaitEvent(m->copy, produced, 0));
+    if (m->world > 1) {
+        if (!m->barrier) return set_error(BMQ_ERR_ARG, "bmq3d_mg: no stream barrier callback set");
+        if (m->barrier((void *)m->copy, m->ctx) != 0) return set_error(BMQ_ERR_CUDA, "bmq3d_mg: the stream barrier callback failed");
+    }
+    for (int g = 0; g < ngroups; ++g) {
+        for (int q = 0; q < groups[g].n; ++q) {
+            Field *fd = field_of(s, groups[g].ids[q]);
+            if (!fd || !fd->alloc) return set_error(BMQ_ERR_ARG, "bmq3d_mg: bad field id %d in an exchange", groups[g].ids[q]);
+            const int dz = fd->nz - s->nk, w = groups[g].width;
+            int a0, b0;
+            mg_owned(m, dz, m->rank, a0, b0);
+            const int want[2][2] = {{m->rank > 0 ? (a0 - w > 0 ? a0 - w : 0) : 0, m->rank > 0 ? a0 : 0},
+                                    {m->rank < m->world - 1 ? b0 : 0, m->rank < m->world - 1 ? (b0 + w + 1 < fd->nz ? b0 + w + 1 : fd->nz) : 0}};
+            for (int side = 0; side < 2; ++side) {
+                for (int r = 0; r < m->world; ++r) {
+                    if (r == m->rank) continue;
+                    int qa, qb;
+                    mg_owned(m, dz, r, qa, qb);
+                    const int a = want[side][0] > qa ? want[side][0] : qa, b = want[side][1] < qb ? want[side][1] : qb;
+                    if (a >= b) continue;
+                    if (a < fd->p0 || b > fd->p1) return set_error(BMQ_ERR_HALO, "bmq3d_mg: halo planes [%d,%d) are not stored (allocated halo %d)", a, b, s->halo);
+                    const int k0r = mg_slab_k0(s->nk, m->world, r);
+                    const int q0 = k0r - s->halo > 0 ? k0r - s->halo : 0;     // first plane rank r stores (same halo everywhere)
+                    const char *src = (const char *)m->peer[r][fd->alloc_id] + sizeof(float) * fd->plane() * (size_t)(a - q0);
+                    char *dst = (char *)fd->alloc + sizeof(float) * fd->plane() * (size_t)(a - fd->p0);
+                    BMQ_CK(cudaMemcpyAsync(dst, src, sizeof(float) * fd->plane() * (size_t)(b - a), cudaMemcpyDefault, m->copy));
+                    m->stats.bytes_exchanged += (long long)(sizeof(float) * fd->plane() * (size_t)(b - a));
+                }
+            }
+        }
+    }
+    *done = mg_event(m);
+    BMQ_CK(cudaEventRecord(*done, m->copy));
+    m->stats.exchanges++;
+    return BMQ_OK;
+}
+int mg_wait(bmq3d_mg *m, cudaEvent_t done) { BMQ_CK(cudaStreamWaitEvent(m->s->stream, done, 0)); return BMQ_OK; }
+int mg_exchange(bmq3d_mg *m, const MgGroup *groups, int ngroups)
+{
+    cudaEvent_t done;
+    RET_IF(mg_post(m, groups, ngroups, &done));
+    return mg_wait(m, done);
+}
+
+int mg_reduce(bmq3d_mg *m, float *vals, int n)
+{
+    if (m->world == 1) return BMQ_OK;
+    if (!m->allreduce) return set_error(BMQ_ERR_ARG, "bmq3d_mg: no all-reduce callback set");
+    if (m->allreduce(vals, n, m->ctx) != 0) return set_error(BMQ_ERR_CUDA, "bmq3d_mg: the all-reduce callback failed");
+    return BMQ_OK;
+}
+
+const int kVel[3] = {BMQ_F_U, BMQ_F_V, BMQ_F_W};
+const int kInitV[3] = {BMQ_F_U_INIT, BMQ_F_V_INIT, BMQ_F_W_INIT}, kInitS[2] = {BMQ_F_RHO_INIT, BMQ_F_T_INIT};
+const int kPrevV[3] = {BMQ_F_U_PREV, BMQ_F_V_PREV, BMQ_F_W_PREV}, kPrevS[2] = {BMQ_F_RHO_PREV, BMQ_F_T_PREV};
+const int kAdvV[3] = {BMQ_F_U_ADV, BMQ_F_V_ADV, BMQ_F_W_ADV}, kAdvS[2] = {BMQ_F_RHO_ADV, BMQ_F_T_ADV};
+const int kErrV[3] = {BMQ_F_U_ERR, BMQ_F_V_ERR, BMQ_F_W_ERR}, kErrS[2] = {BMQ_F_RHO_ERR, BMQ_F_T_ERR};
+const int kChV[6] = {BMQ_F_DU_EXT, BMQ_F_DV_EXT, BMQ_F_DW_EXT, BMQ_F_DU_PROJ, BMQ_F_DV_PROJ, BMQ_F_DW_PROJ};
+const int kChS[2] = {BMQ_F_DRHO_EXT, BMQ_F_DT_EXT};
+const int kBwdV[3] = {BMQ_F_VBWD_X, BMQ_F_VBWD_Y, BMQ_F_VBWD_Z}, kBwdS[3] = {BMQ_F_SBWD_X, BMQ_F_SBWD_Y, BMQ_F_SBWD_Z};
+const int kFwdV[3] = {BMQ_F_VFWD_X, BMQ_F_VFWD_Y, BMQ_F_VFWD_Z}, kFwdS[3] = {BMQ_F_SFWD_X, BMQ_F_SFWD_Y, BMQ_F_SFWD_Z};
+const int kBwdpV[3] = {BMQ_F_VBWDP_X, BMQ_F_VBWDP_Y, BMQ_F_VBWDP_Z}, kBwdpS[3] = {BMQ_F_SBWDP_X, BMQ_F_SBWDP_Y, BMQ_F_SBWDP_Z};
+
+void mg_unmap(bmq3d_mg *m)
+{
+    for (int r = 0; r < (int)m->peer.size(); ++r) {
+        if (r < (int)m->peer_is_ipc.size() && m->peer_is_ipc[r])
+            for (void *p : m->peer[r]) if (p) cudaIpcCloseMemHandle(p);
+        m->peer[r].clear();
+    }
+    m->peer.clear();
+    m->peer_is_ipc.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmq3d_mg_create(int ni, int nj, int nk, float h, float blend_coeff, int rank, int world, int halo, bmq3d_mg **out)
+{
+    if (!out) return set_error(BMQ_ERR_ARG, "bmq3d_mg_create: out is null");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world || nk / world < 1)
+        return set_error(BMQ_ERR_ARG, "bmq3d_mg_create: bad rank %d of %d for %d planes", rank, world, nk);
+    bmq3d_mg *m = new (std::nothrow) bmq3d_mg();
+    if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_create: out of host memory");
+    m->rank = rank; m->world = world;
+    memset(&m->stats, 0, sizeof m->stats);
+    if (halo > nk) halo = nk;
+    int st = bmq3d_create_slab(ni, nj, nk, h, blend_coeff, mg_slab_k0(nk, world, rank), mg_slab_k0(nk, world, rank + 1), world > 1 ? halo : 0, &m->s);
+    if (st == BMQ_OK) st = check_cuda(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__);
+    for (int e = 0; e < MG_EVENTS && st == BMQ_OK; ++e)
+        st = check_cuda(cudaEventCreateWithFlags(&m->ev[e], cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
+    if (st != BMQ_OK) { bmq3d_mg_destroy(m); return st; }
+    m->stats.halo_allocated = m->s->halo;
+    *out = m;
+    return BMQ_OK;
+}
+
+int bmq3d_mg_destroy(bmq3d_mg *m)
+{
+    if (!m) return BMQ_OK;
+    if (m->copy) cudaStreamSynchronize(m->copy);
+    mg_unmap(m);
+    for (auto e : m->ev) if (e) cudaEventDestroy(e);
+    if (m->copy) cudaStreamDestroy(m->copy);
+    if (m->s) bmq3d_destroy(m->s);
+    delete m;
+    return BMQ_OK;
+}
+
+int bmq3d_mg_solver(bmq3d_mg *m, bmq3d_solver **out)
+{
+    if (!m || !out) return set_error(BMQ_ERR_ARG, "bmq3d_mg_solver: null argument");
+    *out = m->s;
+    return BMQ_OK;
+}
+
+int bmq3d_mg_set_collectives(bmq3d_mg *m, bmq_allreduce_max_fn allreduce_max, bmq_stream_barrier_fn stream_barrier, void *ctx)
+{
+    if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_set_collectives: null handle");
+    m->allreduce = allreduce_max; m->barrier = stream_barrier; m->ctx = ctx;
+    return BMQ_OK;
+}
+
+int bmq3d_mg_export_size(bmq3d_mg *m, size_t *bytes)
+{
+    if (!m || !bytes) return set_error(BMQ_ERR_ARG, "bmq3d_mg_export_size: null argument");
+    *bytes = sizeof(MgBlobHeader) + sizeof(MgBlobEntry) * (size_t)m->s->n_allocs;
+    return BMQ_OK;
+}
+
+int bmq3d_mg_export(bmq3d_mg *m, void *blob)
+{
+    if (!m || !blob) return set_error(BMQ_ERR_ARG, "bmq3d_mg_export: null argument");
+    bmq3d_solver *s = m->s;
+    MgBlobHeader hd{(long long)getpid(), s->n_allocs, s->halo, m->rank, 0};
+    memcpy(blob, &hd, sizeof hd);
+    MgBlobEntry *ent = reinterpret_cast<MgBlobEntry *>((char *)blob + sizeof hd);
+    memset(ent, 0, sizeof(MgBlobEntry) * (size_t)s->n_allocs);
+    auto put = [&](const Field &fd) -> int {
+        if (!fd.alloc || fd.alloc_id < 0) return BMQ_OK;
+        cudaIpcMemHandle_t hnd;
+        BMQ_CK(cudaIpcGetMemHandle(&hnd, fd.alloc));
+        memcpy(ent[fd.alloc_id].ipc, &hnd, 64);
+        ent[fd.alloc_id].raw = fd.alloc;
+        return BMQ_OK;
+    };
+    for (auto &fd : s->f) RET_IF(put(fd));
+    for (auto &fd : s->scratch) RET_IF(put(fd));
+    for (auto &fd : s->tmpmap) RET_IF(put(fd));
+    return BMQ_OK;
+}
+
+int bmq3d_mg_disconnect(bmq3d_mg *m)
+{
+    if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_disconnect: null handle");
+    BMQ_CK(cudaStreamSynchronize(m->copy));
+    BMQ_CK(cudaStreamSynchronize(m->s->stream));
+    mg_unmap(m);
+    return BMQ_OK;
+}
+
+int bmq3d_mg_connect(bmq3d_mg *m, const void *all_blobs)
+{
+    if (!m || !all_blobs) return set_error(BMQ_ERR_ARG, "bmq3d_mg_connect: null argument");
+    size_t one = 0;
+    RET_IF(bmq3d_mg_export_size(m, &one));
+    mg_unmap(m);
+    m->peer.assign(m->world, std::vector<void *>());
+    m->peer_is_ipc.assign(m->world, 0);
+    for (int r = 0; r < m->world; ++r) {
+        if (r == m->rank) continue;
+        const char *blob = (const char *)all_blobs + one * (size_t)r;
+        MgBlobHeader hd;
+        memcpy(&hd, blob, sizeof hd);
+        if (hd.rank != r || hd.n_allocs != m->s->n_allocs || hd.halo != m->s->halo)
+            return set_error(BMQ_ERR_ARG, "bmq3d_mg_connect: blob %d does not match (rank %d, %d allocations, halo %d)", r, hd.rank, hd.n_allocs, hd.halo);
+        const MgBlobEntry *ent = reinterpret_cast<const MgBlobEntry *>(blob + sizeof hd);
+        m->peer[r].assign(hd.n_allocs, nullptr);
+        const bool same_process = hd.pid == (long long)getpid();
+        m->peer_is_ipc[r] = same_process ? 0 : 1;
+        for (int a = 0; a < hd.n_allocs; ++a) {
+            if (!ent[a].raw) continue;
+            if (same_process) { m->peer[r][a] = ent[a].raw; continue; }
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, ent[a].ipc, 64);
+            BMQ_CK(cudaIpcOpenMemHandle(&m->peer[r][a], hnd, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    return BMQ_OK;
+}
+
+int bmq3d_mg_grow_halo(bmq3d_mg *m, int new_halo)
+{
+    if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_grow_halo: null handle");
+    if (!m->peer.empty()) return set_error(BMQ_ERR_ARG, "bmq3d_mg_grow_halo: disconnect first (peers still map the old buffers)");
+    if (new_halo > m->s->nk) new_halo = m->s->nk;
+    RET_IF(bmq3d_grow_halo(m->s, new_halo));
+    m->stats.halo_allocated = m->s->halo;
+    m->stats.halo_grown++;
+    return BMQ_OK;
+}
+
+// Phase A over z-slabs (zslab.py:ZSlabStepper.advect).  BMQ_ERR_HALO = the allocated halo is narrower than
+// stats.halo_needed: nothing has been modified yet; disconnect, grow, export / connect again and call again.
+int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
+{
+    if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_advect: null handle");
+    if (!(dt > 0.f)) return set_error(BMQ_ERR_ARG, "bmq3d_mg_advect: dt must be positive");
+    bmq3d_solver *s = m->s;
+    if (m->world > 1 && m->peer.empty()) return set_error(BMQ_ERR_ARG, "bmq3d_mg_advect: not connected");
+    float gmax = 0.f;
+    RET_IF(stage_maxvel(s, &gmax));
+    RET_IF(mg_reduce(m, &gmax, 1));
+    set_cfl(s, framenum, gmax);
+    const float cfl_frame = dt * (gmax > 1e-4f ? gmax : 1e-4f) / s->h;
+    int need[2], need_b[2] = {0, 0}, widest = MG_NARROW;
+    bool blend_on[2];
+    for (int q = 0; q < 2; ++q) {
+        need[q] = (int)ceilf(m->disp[q] + cfl_frame) + 3;
+        blend_on[q] = s->blend != 1.0f && m->reinit_count[q] > 0;
+        if (blend_on[q]) need_b[q] = (int)ceilf(m->disp_prev[q] + m->disp[q] + cfl_frame) + 3;
+        widest = need[q] > widest ? need[q] : widest;
+        widest = need_b[q] > widest ? need_b[q] : widest;
+    }
+    m->stats.halo_needed = widest;
+    if (m->world > 1 && widest > s->halo)
+        return set_error(BMQ_ERR_HALO, "bmq3d_mg_advect: need %d halo planes, %d allocated: grow and call again", widest, s->halo);
+    const int wv = m->wv = need[0], ws = m->ws = need[1], wmax = wv > ws ? wv : ws;
+    m->stats.halo_vel = wv; m->stats.halo_scalar = ws;
+    if (m->world == 1) {         // a single rank: the plain phase A
+        return bmq3d_advect(s, framenum, dt, 0);
+    }
+    cudaEvent_t h_init, h_bwd = nullptr, h_fwd, h_av, h_as, h_ev, h_es;
+    { const MgGroup g[1] = {{kVel, 3, wmax}}; RET_IF(mg_exchange(m, g, 1)); }                       // consumers: DMC, forward
+    { const MgGroup g[2] = {{kBwdV, 3, MG_NARROW}, {kBwdS, 3, MG_NARROW}}; RET_IF(mg_exchange(m, g, 2)); }
+    { const MgGroup g[2] = {{kInitV, 3, wv}, {kInitS, 2, ws}}; RET_IF(mg_post(m, g, 2, &h_init)); }   // overlaps DMC + forward
+    float T = 0.f, substep = s->cfldt;
+    int n = 0;
+    while (T < dt) {
+        if (T + substep > dt) substep = dt - T;
+        RET_IF(stage_dmc(s, substep));
+        T += substep;
+        if (++n > 4096) return set_error(BMQ_ERR_ARG, "bmq3d_mg_advect: more than 4096 CFL sub-steps");
+        if (T < dt) { const MgGroup g[2] = {{kBwdV, 3, MG_NARROW}, {kBwdS, 3, MG_NARROW}}; RET_IF(mg_exchange(m, g, 2)); }
+        else { const MgGroup g[2] = {{kBwdV, 3, wv}, {kBwdS, 3, ws}}; RET_IF(mg_post(m, g, 2, &h_bwd)); }   // overlaps forward
+    }
+    s->stats.n_substeps = n;
+    RET_IF(stage_forward(s, dt));
+    { const MgGroup g[2] = {{kFwdV, 3, wv}, {kFwdS, 3, ws}}; RET_IF(mg_post(m, g, 2, &h_fwd)); }      // overlaps advect
+    if (h_bwd) RET_IF(mg_wait(m, h_bwd));
+    RET_IF(mg_wait(m, h_init));
+    RET_IF(stage_advect(s, 0));
+    { const MgGroup g[1] = {{kAdvV, 3, wv}}; RET_IF(mg_post(m, g, 1, &h_av)); }
+    RET_IF(stage_advect(s, 1));
+    { const MgGroup g[1] = {{kAdvS, 2, ws}}; RET_IF(mg_post(m, g, 1, &h_as)); }
+    RET_IF(mg_wait(m, h_fwd));
+    RET_IF(mg_wait(m, h_av));
+    RET_IF(stage_error(s, 0));
+    { const MgGroup g[1] = {{kErrV, 3, wv}}; RET_IF(mg_post(m, g, 1, &h_ev)); }
+    RET_IF(mg_wait(m, h_as));
+    RET_IF(stage_error(s, 1));
+    { const MgGroup g[1] = {{kErrS, 2, ws}}; RET_IF(mg_post(m, g, 1, &h_es)); }
+    RET_IF(mg_wait(m, h_ev));
+    RET_IF(stage_apply(s, 0));
+    RET_IF(mg_wait(m, h_es));
+    RET_IF(stage_apply(s, 1));
+    for (int which = 0; which < 2; ++which) {
+        if (!blend_on[which]) continue;
+        const MgGroup g[2] = {{which ? kPrevS : kPrevV, which ? 2 : 3, need_b[which]}, {which ? kBwdpS : kBwdpV, 3, need_b[which]}};
+        RET_IF(mg_exchange(m, g, 2));
+        RET_IF(stage_blend(s, which));
+    }
+    return BMQ_OK;
+}
+
+// Phase B over z-slabs (zslab.py:ZSlabStepper.accumulate)
+int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt)
+{
+    if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_accumulate: null handle");
+    bmq3d_solver *s = m->s;
+    cudaEvent_t h_ch = nullptr;
+    if (m->world > 1) {
+        const MgGroup g[2] = {{kChV, 6, m->wv}, {kChS, 2, m->ws}};
+        RET_IF(mg_post(m, g, 2, &h_ch));                                                             // overlaps the distortion kernel
+    }
+    float red[4] = {0, 0, 0, 0};
+    RET_IF(stage_distortion(s, &red[0], &red[1], &red[2]));     // red[2], red[3] = z displacement per mapper
+    RET_IF(mg_reduce(m, red, 4));
+    m->disp[0] = red[2]; m->disp[1] = red[3];
+    s->stats.max_disp_z_vel = red[2]; s->stats.max_disp_z_scalar = red[3];
+    s->stats.max_disp_z = red[2] > red[3] ? red[2] : red[3];
+    decide(s, framenum, dt, red[0], red[1]);
+    if (h_ch) RET_IF(mg_wait(m, h_ch));
+    RET_IF(stage_accumulate(s, 0));
+    RET_IF(stage_accumulate(s, 1));
+    if (s->vel_reinit) {
+        RET_IF(stage_reinit(s, 0, 0));
+        RET_IF(stage_reinit(s, 0, 1));
+        m->reinit_count[0]++;
+        m->disp_prev[0] = m->disp[0]; m->disp[0] = 0.f;
+    }
+    if (s->scalar_reinit) {
+        RET_IF(stage_reinit(s, 1, 0));
+        m->reinit_count[1]++;
+        m->disp_prev[1] = m->disp[1]; m->disp[1] = 0.f;
+    }
+    s->stats.vel_reinit_count = s->vel_reinit_count;
+    s->stats.scalar_reinit_count = s->scalar_reinit_count;
+    return BMQ_OK;
+}
+
+int bmq3d_mg_get_stats(bmq3d_mg *m, bmq3d_mg_stats *out)
+{
+    if (!m || !out) return set_error(BMQ_ERR_ARG, "bmq3d_mg_get_stats: null argument");
+    *out = m->stats;
     return BMQ_OK;
 }
 

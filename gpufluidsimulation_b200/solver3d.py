@@ -232,11 +232,17 @@ class BimocqAdvection3D:
 
     CURRENT = ("U", "V", "W", "RHO", "T")
 
-    def __init__(self, ni, nj, nk, h, blend_coeff=1.0, slab=None, halo=0):
+    def __init__(self, ni, nj, nk, h, blend_coeff=1.0, slab=None, halo=0, borrowed_handle=None):
+        """borrowed_handle: wrap an existing bmq3d_solver* (e.g. the slab handle a bmq3d_mg owns) instead of
+        creating one; close() then leaves it alone."""
         _torch()
         self.lib = load_library()
         self.ni, self.nj, self.nk = ni, nj, nk
         self.h = float(np.float32(h))
+        self._owned = borrowed_handle is None
+        if borrowed_handle is not None:
+            self._h = borrowed_handle
+            return
         self._h = C.c_void_p()
         k0, k1 = slab if slab is not None else (0, nk)
         check(self.lib.bmq3d_create_slab(ni, nj, nk, self.h, float(blend_coeff), k0, k1, halo, C.byref(self._h)),
@@ -244,7 +250,8 @@ class BimocqAdvection3D:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
-            self.lib.bmq3d_destroy(self._h)
+            if self._owned:
+                self.lib.bmq3d_destroy(self._h)
             self._h = None
 
     def __del__(self):

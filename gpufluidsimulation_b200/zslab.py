@@ -433,8 +433,9 @@ class ZSlabStepper:
         self.prof = {}
         if self.profile:
             ex, red, exa = comm.exchange, comm.allreduce_max, comm.exchange_async
-            comm.exchange = lambda *a: self._timed("exchange", lambda: ex(*a))
-            comm.exchange_async = lambda *a: self._timed("exchange_async_post", lambda: exa(*a))
+            # keyed by the first field of the exchange, so that the profile names the exchange that costs most
+            comm.exchange = lambda *a: self._timed("exchange(blocking):" + a[1][0][0][0], lambda: ex(*a))
+            comm.exchange_async = lambda *a: self._timed("exchange(posted, then synchronised by the profiler):" + a[1][0][0][0], lambda: exa(*a))
             comm.allreduce_max = lambda *a: self._timed("allreduce", lambda: red(*a))
             each = self._each
             self._each = lambda fn: self._timed("stages", lambda: each(fn))
@@ -565,6 +566,163 @@ class ZSlabStepper:
 
 
 # ----------------------------------------------------------------------------------------------
+# the same step inside the library: bmq3d_mg_* (include/bimocq_b200.h), driven from here with
+# torch.distributed supplying the two collectives the C layer asks its host for
+# ----------------------------------------------------------------------------------------------
+class NativeSlab:
+    """One rank of the C-level z-slab driver.  `collectives` = (allreduce_max(list[float]) -> list[float],
+    stream_barrier(cuda_stream_ptr), host_barrier(), all_gather_bytes(bytes) -> list[bytes])."""
+
+    def __init__(self, ni, nj, nk, h, blend, rank, world, halo, collectives):
+        from . import capi
+        from .solver3d import BimocqAdvection3D
+        self.capi, self.lib = capi, capi.load_library()
+        self.ni, self.nj, self.nk, self.rank, self.world = ni, nj, nk, rank, world
+        self.k0, self.k1 = slab_bounds(nk, world, rank)
+        self.h = float(np.float32(h))
+        self.allreduce_max, self.stream_barrier, self.host_barrier, self.all_gather_bytes = collectives
+        self._mg = C.c_void_p()
+        capi.check(self.lib.bmq3d_mg_create(ni, nj, nk, self.h, float(blend), rank, world, int(halo), C.byref(self._mg)), "bmq3d_mg_create")
+        sh = C.c_void_p()
+        capi.check(self.lib.bmq3d_mg_solver(self._mg, C.byref(sh)), "bmq3d_mg_solver")
+        self.solver = BimocqAdvection3D(ni, nj, nk, h, blend, borrowed_handle=sh)
+        self.error = None
+
+        def _reduce(vals, n, _ctx):
+            try:
+                out = self.allreduce_max([vals[q] for q in range(n)])
+                for q in range(n):
+                    vals[q] = out[q]
+                return 0
+            except BaseException as exc:   # noqa: BLE001 -- must not unwind through C
+                self.error = exc
+                return 1
+
+        def _barrier(stream, _ctx):
+            try:
+                self.stream_barrier(stream)
+                return 0
+            except BaseException as exc:   # noqa: BLE001
+                self.error = exc
+                return 1
+
+        self._cb = (capi.ALLREDUCE_MAX_FN(_reduce), capi.STREAM_BARRIER_FN(_barrier))     # keep them alive
+        capi.check(self.lib.bmq3d_mg_set_collectives(self._mg, self._cb[0], self._cb[1], None), "bmq3d_mg_set_collectives")
+        self.connect()
+
+    @property
+    def halo(self):
+        return self.mg_stats()["halo_allocated"]
+
+    def connect(self):
+        if self.world == 1:
+            return
+        n = C.c_size_t()
+        self.capi.check(self.lib.bmq3d_mg_export_size(self._mg, C.byref(n)), "bmq3d_mg_export_size")
+        blob = (C.c_ubyte * n.value)()
+        self.capi.check(self.lib.bmq3d_mg_export(self._mg, blob), "bmq3d_mg_export")
+        everyone = b"".join(self.all_gather_bytes(bytes(blob)))
+        assert len(everyone) == n.value * self.world
+        self.capi.check(self.lib.bmq3d_mg_connect(self._mg, everyone), "bmq3d_mg_connect")
+
+    def _check(self, status, what):
+        if status != 0 and self.error is not None:
+            err, self.error = self.error, None
+            raise err
+        self.capi.check(status, what)
+
+    def advect(self, frame, dt):
+        dt = float(np.float32(dt))
+        st = self.lib.bmq3d_mg_advect(self._mg, int(frame), dt)
+        if st == 3:      # BMQ_ERR_HALO: every rank sees it in the same call (the width comes from all-reduced numbers)
+            self.lib.bmq_clear_error()
+            need = self.mg_stats()["halo_needed"]
+            self.capi.check(self.lib.bmq3d_mg_disconnect(self._mg), "bmq3d_mg_disconnect")
+            self.host_barrier()      # nobody frees a buffer that a peer still has mapped
+            self.capi.check(self.lib.bmq3d_mg_grow_halo(self._mg, need + GROW_SLACK), "bmq3d_mg_grow_halo")
+            self.connect()
+            st = self.lib.bmq3d_mg_advect(self._mg, int(frame), dt)
+        self._check(st, "bmq3d_mg_advect")
+
+    def accumulate(self, frame, dt):
+        self._check(self.lib.bmq3d_mg_accumulate(self._mg, int(frame), float(np.float32(dt))), "bmq3d_mg_accumulate")
+
+    def mg_stats(self):
+        st = self.capi.MgStats()
+        self.capi.check(self.lib.bmq3d_mg_get_stats(self._mg, C.byref(st)), "bmq3d_mg_get_stats")
+        return st.as_dict()
+
+    def field_with_origin(self, name):
+        _, p0, _, _, _ = self.solver.field_info(name)
+        return self.solver.field(name), p0
+
+    def close(self):
+        if self._mg:
+            self.solver.close()
+            self.lib.bmq3d_mg_destroy(self._mg)
+            self._mg = None
+
+
+class _NativeStepper:
+    """What bench.py and the tests read off a stepper, for the native driver."""
+
+    def __init__(self, slab):
+        self.slab, self.prof, self.profile, self.stats = slab, {}, False, {}
+
+    @property
+    def halo(self):
+        return self.slab.halo
+
+    @property
+    def grow_count(self):
+        return self.slab.mg_stats()["halo_grown"]
+
+    def advect(self, frame, dt):
+        self.slab.advect(frame, dt)
+        st = self.slab.mg_stats()
+        self.stats.update(halo_used=max(st["halo_vel"], st["halo_scalar"]), halo_vel=st["halo_vel"], halo_scalar=st["halo_scalar"],
+                          halo_allocated=st["halo_allocated"], n_substeps=self.slab.solver.stats()["n_substeps"])
+
+    def accumulate(self, frame, dt):
+        self.slab.accumulate(frame, dt)
+        st = self.slab.solver.stats()
+        self.stats.update(vel_reinit=bool(st["vel_reinit"]), scalar_reinit=bool(st["scalar_reinit"]), max_disp_z=st["max_disp_z"],
+                          disp_z_vel=st["max_disp_z_vel"], disp_z_scalar=st["max_disp_z_scalar"], halo_grown=self.grow_count)
+
+
+def torch_collectives(device):
+    """The collectives NativeSlab needs, on torch.distributed (NCCL)."""
+    import torch
+    import torch.distributed as dist
+    flag = torch.zeros(1, dtype=torch.float32, device=device)
+    streams = {}
+
+    def allreduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def stream_barrier(stream_ptr):
+        st = streams.get(stream_ptr)
+        if st is None:
+            st = streams[stream_ptr] = torch.cuda.ExternalStream(stream_ptr, device=device)
+        with torch.cuda.stream(st):
+            dist.all_reduce(flag)
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def all_gather_bytes(b):
+        mine = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(device)
+        out = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, mine)
+        return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+    return allreduce_max, stream_barrier, host_barrier, all_gather_bytes
+
+
+# ----------------------------------------------------------------------------------------------
 # user-facing wrapper for one process per GPU (bench.py, multi-GPU tests)
 # ----------------------------------------------------------------------------------------------
 class ZSlabAdvection3D:
@@ -572,7 +730,8 @@ class ZSlabAdvection3D:
                  cfl_frame=1.5):
         """halo: planes allocated on both sides of the slab; None = default_halo(cfl_frame), the
         reach of the scalar mapper's 30-frame re-initialisation cap (it grows on demand anyway).
-        transport: "peer" = direct P2P copies of peer-mapped memory over NVLink (PeerComm; if the
+        transport: "native" = the C-level driver bmq3d_mg_* (peer copies over NVLink issued by the library;
+        torch.distributed supplies the scalar all-reduce and the stream barrier), "peer" = direct P2P copies of peer-mapped memory over NVLink (PeerComm; if the
         peer mapping cannot be set up on every rank, all ranks fall back to NCCL and say so on
         stderr), "nccl" = NCCL send/recv (DistComm)."""
         import torch
@@ -581,9 +740,16 @@ class ZSlabAdvection3D:
         if halo is None:
             halo = default_halo(cfl_frame)
         halo = min(int(halo), nk)
-        self.r = CudaSlabRank(ni, nj, nk, h, blend_coeff, rank, world, halo)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.transport = transport
+        if transport == "native":
+            # the whole z-slab step inside the library (bmq3d_mg_*); torch.distributed only supplies the collectives
+            self.r = NativeSlab(ni, nj, nk, h, blend_coeff, rank, world, halo, torch_collectives(dev))
+            self.comm = None
+            self.stepper = _NativeStepper(self.r)
+            self.lib = self.r.solver.lib
+            return
+        self.r = CudaSlabRank(ni, nj, nk, h, blend_coeff, rank, world, halo)
         if transport == "peer":
             try:
                 self.comm = PeerComm(world, rank, dev, self.r)
@@ -685,6 +851,11 @@ class ZSlabAdvection3D:
         return self.r.solver.timing_read()
 
     def close(self):
+        if self.comm is None:                 # native driver: unmap the peers before anybody frees
+            self.torch.cuda.synchronize()
+            self.dist_barrier()
+            self.r.close()
+            return
         if hasattr(self.comm, "close"):
             self.torch.cuda.synchronize()
             self.dist_barrier()

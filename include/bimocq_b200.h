@@ -350,6 +350,48 @@ enum { BMQ_F_U_ADV = 64, BMQ_F_V_ADV, BMQ_F_W_ADV, BMQ_F_RHO_ADV, BMQ_F_T_ADV,
        /* the six DMC ping-pong buffers (they rotate with the backward maps) */
        BMQ_F_TMPMAP0 = 80, BMQ_F_TMPMAP1, BMQ_F_TMPMAP2, BMQ_F_TMPMAP3, BMQ_F_TMPMAP4, BMQ_F_TMPMAP5 };
 
+/* ------------------------------------------------------------------ z-slab decomposition over the GPUs of one box
+ * The reference has no multi-GPU path; this is the new domain decomposition of BASELINE.json's
+ * north_star behind a C API, so that a C++ host (one process, or one thread, per GPU) can drive it.  Rank r owns
+ * the global planes [r*nk/world, (r+1)*nk/world) and stores `halo` more on both sides; kernels work on global
+ * indices, so every rank computes bit for bit what a single GPU computes.  Halos are PULLED out of their owners'
+ * memory with stream-ordered peer copies over NVLink (CUDA IPC mappings; raw pointers inside one process);
+ * widths follow the measured z-displacement of each mapper's maps (velocity mapper: reinitialised at least every
+ * 10 frames, scalar mapper every 30) and may reach past the neighbouring slab.
+ *
+ * Set-up:   bmq3d_mg_create on every rank; fill the fields through bmq3d_mg_solver + bmq3d_upload / bmq3d_field_ptr;
+ *           bmq3d_reset; bmq3d_mg_export -> all-gather the blobs with whatever the host has (MPI, NCCL, files) ->
+ *           bmq3d_mg_connect(all blobs, rank order); bmq3d_mg_set_collectives.
+ * Per step: bmq3d_mg_advect; the caller's forces / projection on its own planes (change fields D*_EXT, D*_PROJ);
+ *           bmq3d_mg_accumulate.
+ * BMQ_ERR_HALO from bmq3d_mg_advect = the allocated halo is narrower than stats.halo_needed (nothing has been
+ *           modified): on EVERY rank (the decision derives from all-reduced numbers) bmq3d_mg_disconnect, a host
+ *           barrier, bmq3d_mg_grow_halo, export / all-gather / connect again, call bmq3d_mg_advect again. */
+typedef struct bmq3d_mg bmq3d_mg;
+/* in-place max all-reduce of n floats over all ranks (blocking); 0 = success */
+typedef int (*bmq_allreduce_max_fn)(float *vals, int n, void *ctx);
+/* a barrier over all ranks ORDERED IN `cuda_stream`: work queued on that stream afterwards starts only when every
+ * rank's work queued on its stream before its own call has completed (e.g. a one-element ncclAllReduce on that
+ * stream).  Must not block the host on the device; 0 = success */
+typedef int (*bmq_stream_barrier_fn)(void *cuda_stream, void *ctx);
+typedef struct bmq3d_mg_stats {
+    int halo_allocated, halo_needed, halo_vel, halo_scalar;   /* planes: allocated; widest needed; exchanged last step per mapper */
+    int halo_grown;                                           /* number of bmq3d_mg_grow_halo calls */
+    long long exchanges, bytes_exchanged;                     /* since creation */
+} bmq3d_mg_stats;
+int bmq3d_mg_create(int ni, int nj, int nk, float h, float blend_coeff, int rank, int world, int halo, bmq3d_mg **out);
+int bmq3d_mg_destroy(bmq3d_mg *m);
+int bmq3d_mg_solver(bmq3d_mg *m, bmq3d_solver **out);        /* the rank's slab handle (owned by m) */
+int bmq3d_mg_set_collectives(bmq3d_mg *m, bmq_allreduce_max_fn allreduce_max, bmq_stream_barrier_fn stream_barrier, void *ctx);
+int bmq3d_mg_export_size(bmq3d_mg *m, size_t *bytes);
+int bmq3d_mg_export(bmq3d_mg *m, void *blob);
+int bmq3d_mg_connect(bmq3d_mg *m, const void *all_blobs);    /* world blobs of bmq3d_mg_export_size bytes, in rank order */
+int bmq3d_mg_disconnect(bmq3d_mg *m);
+int bmq3d_mg_grow_halo(bmq3d_mg *m, int new_halo);
+int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt);
+int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt);
+int bmq3d_mg_get_stats(bmq3d_mg *m, bmq3d_mg_stats *out);
+
 /* ------------------------------------------------------------------ handle API (2D)
  * The 2D reference (src/bimocq2D) is CPU code with no device seam; this API is the seam behind
  * BimocqSolver2D::advanceBIMOCQ (bimocq2D/BimocqSolver2D.cpp:390-508), whose signature

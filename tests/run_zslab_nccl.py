@@ -22,7 +22,7 @@ def main():
     dev = torch.device("cuda", local)
     u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0, xp=torch, device=dev)
     u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
-    for transport in ("peer", "nccl"):
+    for transport in ("native", "peer", "nccl"):
         run(transport, rank, world, ni, nj, nk, h, halo, frames, dt, u, v, w, rho, T)
     dist.barrier()
     if rank == 0:

@@ -145,6 +145,92 @@ def test_forty_frames_with_growing_displacement(cuda, world, blend):
     single.close()
 
 
+def test_native_driver_with_logical_ranks_in_threads(cuda):
+    """bmq3d_mg_* (the z-slab driver inside the library) with three logical ranks on one GPU, one host thread per
+    rank as a C++ host would run them: peers are mapped by raw pointer (same process), the two collectives the
+    library asks for are thread barriers.  Halo starts too narrow, so BMQ_ERR_HALO -> disconnect / grow /
+    reconnect is exercised.  Owned planes bit-identical to a single GPU."""
+    import threading
+
+    from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
+    torch = cuda
+    ni, nj, nk, dt, world, frames, blend = 32, 28, 45, 0.02, 3, 8, 0.5
+    h = 1.0 / ni
+    u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0)
+    u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
+    full = (u, v, w, rho, T)
+    single = BimocqAdvection3D(ni, nj, nk, h, blend)
+    single.set_initial(*full)
+    want = []
+    for frame in range(frames):
+        single.advect(frame, dt); single.apply_buoyancy(0.2, dt); single.accumulate(frame, dt)
+        want.append(({n: single.download(n) for n in CHECK}, single.stats()))
+    single.close()
+
+    bar = threading.Barrier(world)
+    slots, blobs, errors, grown = [None] * world, [None] * world, [], [0] * world
+
+    def collectives(rank):
+        def allreduce_max(vals):
+            slots[rank] = list(vals)
+            bar.wait()
+            out = [max(c) for c in zip(*slots)]
+            bar.wait()
+            return out
+
+        def stream_barrier(_stream):
+            torch.cuda.synchronize()
+            bar.wait()
+
+        def host_barrier():
+            torch.cuda.synchronize()
+            bar.wait()
+
+        def all_gather_bytes(b):
+            blobs[rank] = b
+            bar.wait()
+            out = list(blobs)
+            bar.wait()
+            return out
+        return allreduce_max, stream_barrier, host_barrier, all_gather_bytes
+
+    def run(rank):
+        try:
+            r = zslab.NativeSlab(ni, nj, nk, h, blend, rank, world, 4, collectives(rank))
+            for name, a in zip(zslab.CUR, full):
+                _, p0, npl, _, _ = r.solver.field_info(name)
+                r.solver.upload(name, a[p0:p0 + npl])
+            r.solver.reset()
+            for frame in range(frames):
+                r.advect(frame, dt)
+                r.solver.apply_buoyancy(0.2, dt)
+                r.accumulate(frame, dt)
+                torch.cuda.synchronize()
+                st = r.solver.stats()
+                ref, rst = want[frame]
+                assert (st["vel_reinit"], st["scalar_reinit"]) == (rst["vel_reinit"], rst["scalar_reinit"]), frame
+                for name in CHECK:
+                    dz = 1 if name in zslab.W_TYPE else 0
+                    kb, ke = r.k0, r.k1 + (1 if dz and r.k1 == nk else 0)
+                    got, p0 = r.field_with_origin(name)
+                    assert np.array_equal(got[kb - p0:ke - p0].cpu().numpy(), ref[name][kb:ke]), (frame, name, rank)
+                bar.wait()
+            grown[rank] = r.mg_stats()["halo_grown"]
+            bar.wait()       # nobody destroys buffers a peer may still be pulling from
+            r.close()
+        except BaseException as exc:   # noqa: BLE001
+            errors.append((rank, exc))
+            bar.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert all(g >= 1 for g in grown), grown
+
+
 def test_nccl_two_processes(cuda):
     if cuda.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
