@@ -217,13 +217,13 @@ def alg_bytes_per_launch(n, world):
     }
 
 
-def make_solver(n, L, world, rank, args):
+def make_solver(n, L, world, rank, args, blend=1.0):
     from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
     h = L / n
     if world > 1:
         from gpufluidsimulation_b200.zslab import ZSlabAdvection3D
-        return ZSlabAdvection3D(n, n, n, h, 1.0, rank=rank, world=world, halo=args.halo, transport=args.transport, cfl_frame=CFL)
-    return BimocqAdvection3D(n, n, n, h, 1.0)
+        return ZSlabAdvection3D(n, n, n, h, blend, rank=rank, world=world, halo=args.halo, transport=args.transport, cfl_frame=CFL)
+    return BimocqAdvection3D(n, n, n, h, blend)
 
 
 def timed_steps(solver, torch, dist, world, dev, steps, warmup, beta=1e-2, on_timed_start=None):
@@ -267,12 +267,12 @@ def timed_steps(solver, torch, dist, world, dev, steps, warmup, beta=1e-2, on_ti
     return ms, float(np.mean(nsub)), stage, frame
 
 
-def short_run(torch, dist, world, rank, dev, args, kind, n, L, steps=8, warmup=3):
+def short_run(torch, dist, world, rank, dev, args, kind, n, L, steps=8, warmup=3, blend=1.0):
     """One of the other workloads, briefly: ms/step, cell-updates/s, whole-step roofline fraction."""
-    solver = make_solver(n, L, world, rank, args)
+    solver = make_solver(n, L, world, rank, args, blend)
     solver.set_initial_device(*make_scene(kind, n, L, torch, dev))
     torch.cuda.empty_cache()
-    ms, n_sub, _, _ = timed_steps(solver, torch, dist, world, dev, steps, warmup)
+    ms, n_sub, stage, _ = timed_steps(solver, torch, dist, world, dev, steps, warmup)
     st = solver.stats()
     solver.close()
     torch.cuda.empty_cache()
@@ -282,6 +282,10 @@ def short_run(torch, dist, world, rank, dev, args, kind, n, L, steps=8, warmup=3
            "n_sub_mean": n_sub, "hbm_roofline_frac": alg_bytes_per_cell(n_sub) * rate / 1e9 / (peak * world)}
     if world > 1:
         out["halo_vel_scalar_allocated"] = [st.get("halo_vel"), st.get("halo_scalar"), st.get("halo_allocated")]
+    if blend != 1.0:
+        out["blend_coeff"] = blend
+        out["two_level_blend_ms_per_step"] = (stage.get("blend_velocity", (0, 0))[0] + stage.get("blend_scalars", (0, 0))[0]) / steps
+        out["vel_reinit_count"] = st.get("vel_reinit_count")
     return out
 
 
@@ -413,6 +417,9 @@ def run_gpu(args):
                     wn, wkind, _ = WORKLOADS[wname]
                     others[wname] = short_run(torch, dist, world, rank, dev, args, wkind, wn, 1.0)
             extras["workloads"] = others
+            # the two-level map blend (doubleAdvect_kernel, Mapping.cpp:196-201): off in every shipped scene (blend_coeff = 1),
+            # timed here at 0.5 over enough steps for the velocity mapper to have been reinitialised
+            leg("blend_0.5", lambda: short_run(torch, dist, world, rank, dev, args, "plume", 256, 1.0, steps=14, warmup=12, blend=0.5))
             leg("reference_gpu", lambda: measure_reference_gpu(torch))
             if not args.no_2d:
                 leg("bimocq2d", lambda: measure_2d(torch))
