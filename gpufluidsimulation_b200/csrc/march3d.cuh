@@ -128,14 +128,40 @@ struct Split2 {
     float2 f, omf;
     int i0, i1;
 };
-// (cell, fraction, 1 - fraction) of two coordinates at once: q - floor(q) and 1 - f as exact FFMA2s with -1
+// (cell, fraction, 1 - fraction) of two coordinates at once: q - floor(q) and 1 - f as exact FFMA2s with -1.
+// BMQ_SPLIT_MODE selects how floor and the integer cell index are obtained (0 <= q < 2^22 here: positions are
+// clamped to the domain).  All three give the same bits; they load different pipes:
+//   0: FRND.FLOOR + F2I            (two conversions on the narrow XU pipe per coordinate)
+//   1: F2I.FLOOR, floor as float from the integer by exponent splicing: (2^23 | i) - 2^23   (one XU op)
+//   2: no conversion at all: RN(q) = (q + 2^23) - 2^23, floor = RN(q) - (RN(q) > q), index from the mantissa bits
+// measured per 512^3 step: 0 -> 79.5 ms, 1 -> 78.6 ms, 2 -> 83.0 ms (profiles/r2_march_variants.md)
+#ifndef BMQ_SPLIT_MODE
+#define BMQ_SPLIT_MODE 1
+#endif
+__device__ __forceinline__ void floor_index(float q, float &fl, int &i)
+{
+#if BMQ_SPLIT_MODE == 1
+    i = __float2int_rd(q);
+    fl = __fadd_rn(__int_as_float(0x4B000000 | i), -8388608.0f);
+#elif BMQ_SPLIT_MODE == 2
+    const float t = __fadd_rn(q, 8388608.0f);            // integer-valued float in [2^23, 2^24): RN(q) + 2^23
+    const float r = __fadd_rn(t, -8388608.0f);           // RN(q), exact
+    const bool up = r > q;                                 // rounded up: floor is one less
+    i = (__float_as_int(t) - 0x4B000000) - (up ? 1 : 0);
+    fl = up ? __fadd_rn(r, -1.0f) : r;
+#else
+    fl = floorf(q);
+    i = (int)fl;
+#endif
+}
+
 __device__ __forceinline__ Split2 split2(float2 q)
 {
-    const float2 fl = make_float2(floorf(q.x), floorf(q.y));
-    const float2 m1 = make_float2(-1.0f, -1.0f), one = make_float2(1.0f, 1.0f);
+    float2 fl;
     Split2 s;
-    s.i0 = (int)fl.x;
-    s.i1 = (int)fl.y;
+    floor_index(q.x, fl.x, s.i0);
+    floor_index(q.y, fl.y, s.i1);
+    const float2 m1 = make_float2(-1.0f, -1.0f), one = make_float2(1.0f, 1.0f);
 #if defined(BMQ_NO_PACKED_FP32) || defined(BMQ_SPLIT2_SCALAR)
     s.f = make_float2(q.x - fl.x, q.y - fl.y);
     s.omf = make_float2(1.0f - s.f.x, 1.0f - s.f.y);
@@ -176,9 +202,9 @@ __device__ __forceinline__ int gather_one(const float *const (&src)[NS], int sy,
 {
     Frac x, y, z;
     float fl;
-    fl = floorf(qx); x.i = (int)fl; x.f = qx - fl; x.omf = 1.0f - x.f;
-    fl = floorf(qy); y.i = (int)fl; y.f = qy - fl; y.omf = 1.0f - y.f;
-    fl = floorf(qz); z.i = (int)fl; z.f = qz - fl; z.omf = 1.0f - z.f;
+    floor_index(qx, fl, x.i); x.f = qx - fl; x.omf = 1.0f - x.f;
+    floor_index(qy, fl, y.i); y.f = qy - fl; y.omf = 1.0f - y.f;
+    floor_index(qz, fl, z.i); z.f = qz - fl; z.omf = 1.0f - z.f;
     const int o = x.i + sy * y.i + sz * z.i;
 #pragma unroll
     for (int f = 0; f < NS; ++f) out[f] = tri8(src[f] + o, sy, sz, x, y, z);
