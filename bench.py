@@ -367,7 +367,7 @@ def run_gpu(args):
         if world > 1:
             st = solver.stats()
             par = (f"z-slab x{world}, halo {solver.halo} planes allocated (grown {solver.stepper.grow_count}x; last step exchanged "
-                   f"{st.get('halo_vel')} velocity-mapper / {st.get('halo_scalar')} scalar-mapper planes), exchange={solver.transport}")
+                   f"{st.get('halo_vel')} velocity-mapper / {st.get('halo_scalar')} scalar-mapper planes), exchange={solver.transport}" + (f" ({st.get('signalling')})" if st.get("signalling") is not None else ""))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

@@ -86,7 +86,7 @@ FIELD2 = {n: i for i, n in enumerate(FIELD2_NAMES)}
 
 class MgStats(C.Structure):
     _fields_ = [("halo_allocated", _I), ("halo_needed", _I), ("halo_vel", _I), ("halo_scalar", _I), ("halo_grown", _I),
-                ("exchanges", C.c_longlong), ("bytes_exchanged", C.c_longlong)]
+                ("exchanges", C.c_longlong), ("bytes_exchanged", C.c_longlong), ("signalling", _I)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -193,6 +193,7 @@ _PROTOS = {
     "bmq3d_mg_destroy": (_I, [_H]),
     "bmq3d_mg_solver": (_I, [_H, C.POINTER(_H)]),
     "bmq3d_mg_set_collectives": (_I, [_H, ALLREDUCE_MAX_FN, STREAM_BARRIER_FN, C.c_void_p]),
+    "bmq3d_mg_set_signalling": (_I, [_H, _I]),
     "bmq3d_mg_export_size": (_I, [_H, C.POINTER(C.c_size_t)]),
     "bmq3d_mg_export": (_I, [_H, C.c_void_p]),
     "bmq3d_mg_connect": (_I, [_H, C.c_void_p]),

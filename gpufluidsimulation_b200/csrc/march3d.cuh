@@ -38,6 +38,15 @@ enum { GM_ADVECT = 0, GM_ERROR = 1, GM_CUMULATE = 2, GM_APPLY = 3 };
 #ifndef BMQ_MARCH_PREFETCH
 #define BMQ_MARCH_PREFETCH 1    // 1 / 2: prefetch the next cell's new map plane and field plane into L1 / L2
 #endif
+#ifndef BMQ_MARCH_PF_STREAM
+#define BMQ_MARCH_PF_STREAM 1   // prefetch the next cell's streamed (non-gathered) operands (error / accumulate kernels)
+#endif
+#ifndef BMQ_MARCH_PF_ROWS
+#define BMQ_MARCH_PF_ROWS 2     // field rows prefetched around the centre sample's base node (2: j, j+1; 3: also j-1)
+#endif
+#ifndef BMQ_MARCH_PF_DIST
+#define BMQ_MARCH_PF_DIST 2     // field plane prefetched, relative to the centre sample's base plane
+#endif
 
 __device__ __forceinline__ void prefetch_line(const float *p)
 {
@@ -297,6 +306,24 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
         float sum[NS], val[NS];
 #pragma unroll
         for (int f = 0; f < NS; ++f) sum[f] = val[f] = 0.f;
+#if BMQ_MARCH_PF_STREAM
+        // the operands that are streamed rather than gathered (the accumulate target, the error kernel's init) are
+        // compulsory DRAM misses at the end of the cell: ask for the next cell's lines now (ncu: the consumer of the
+        // centre sample shared their scoreboard and waited ~670 cycles; error -5 %, accumulate -1..4 %).  The same
+        // for the apply kernel's next f_adv plane (BMQ_MARCH_PF_STREAM == 2) made that kernel 3-6 % slower.
+        if (k + 1 < klast) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                if (MODE == GM_CUMULATE) prefetch_line(a.out[f] + idx + fplane);
+                if (MODE == GM_ERROR) prefetch_line(a.aux[f] + idx + fplane);
+                if (BMQ_MARCH_PF_STREAM == 2 && MODE == GM_APPLY && k + 2 < fk) {
+                    prefetch_line(a.aux[f] + idx + 2 * fplane);
+                    if (threadIdx.y == 0) prefetch_line(a.aux[f] + idx + 2 * fplane - fi);
+                    if (threadIdx.y == BMQ_MARCH_BY - 1) prefetch_line(a.aux[f] + idx + 2 * fplane + fi);
+                }
+            }
+        }
+#endif
         if (gk) {
             const int onew = mbase + sz * (NZ == 3 ? k + 1 : k);
             Px[SN] = plane_xy<P2, STAG>(m.x + onew, sy, ax, ay);
@@ -354,12 +381,13 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
             const float qcz = to_cells<P2>(clampf(ccz, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
             int zi;
             const int oc = gather_one<NS>(a.src, fi, fplane, qcx, qcy, qcz, val, zi);
-            if (BMQ_MARCH_PREFETCH && k + 1 < kb && zi + 2 < fk) {
+            if (BMQ_MARCH_PREFETCH && k + 1 < kb && zi + BMQ_MARCH_PF_DIST < fk) {
                 // the field plane the next cell's samples will newly touch: two planes above the centre sample's cell
 #pragma unroll
                 for (int f = 0; f < NS; ++f) {
-                    prefetch_line(a.src[f] + oc + 2 * fplane);
-                    prefetch_line(a.src[f] + oc + 2 * fplane + fi);
+                    prefetch_line(a.src[f] + oc + BMQ_MARCH_PF_DIST * fplane);
+                    prefetch_line(a.src[f] + oc + BMQ_MARCH_PF_DIST * fplane + fi);
+                    if (BMQ_MARCH_PF_ROWS == 3) prefetch_line(a.src[f] + oc + BMQ_MARCH_PF_DIST * fplane - fi);
                 }
             }
         }

@@ -13,6 +13,7 @@
 // (Mapping.cpp:430-447, BimocqSolver.cpp:1433-1451).
 #include "common.h"
 #include "launch3d.h"
+#include "mg_signal.h"
 
 #include <cmath>
 #include <cstring>
@@ -177,6 +178,7 @@ struct StageTimer {
 
 // ---- stages ------------------------------------------------------------------------------
 
+// out == nullptr: the result stays in s->d_red[0] (the z-slab driver reduces it over the ranks on the device)
 int stage_maxvel(bmq3d_solver *s, float *out)
 {
     StageTimer _t(s, BMQ_T_MAXVEL);
@@ -187,6 +189,7 @@ int stage_maxvel(bmq3d_solver *s, float *out)
     BMQ_CK(launch_maxabs3(s->stream, u.vbase() + u.plane() * ru.kbeg, u.plane() * (ru.kend - ru.kbeg),
                           v.vbase() + v.plane() * ru.kbeg, v.plane() * (ru.kend - ru.kbeg),
                           w.vbase() + w.plane() * rw.kbeg, w.plane() * (rw.kend - rw.kbeg), s->d_red));
+    if (!out) return BMQ_OK;
     BMQ_CK(cudaMemcpyAsync(s->h_red, s->d_red, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     BMQ_CK(cudaStreamSynchronize(s->stream));
     *out = s->h_red[0];
@@ -359,6 +362,7 @@ int stage_blend(bmq3d_solver *s, int which)
 
 // estimateDistortion for both mappers (Mapping.cpp:91-118) with the max on the device
 // dispz[0], dispz[1]: max |map_z - z| in cells of the velocity / scalar mapper (z-slab halo sizing)
+// vel_d2 == nullptr: the four results stay in s->d_red[1..4] (squared distortions, z displacements in world units)
 int stage_distortion(bmq3d_solver *s, float *vel_d2, float *sca_d2, float *dispz)
 {
     StageTimer _t(s, BMQ_T_DISTORTION);
@@ -372,6 +376,7 @@ int stage_distortion(bmq3d_solver *s, float *vel_d2, float *sca_d2, float *dispz
     float *d2[2] = {s->d_red + 1, s->d_red + 2};
     float *dz[2] = {s->d_red + 3, s->d_red + 4};
     BMQ_CK(launch_estimate(s->stream, s->g, own(s, 0), 2, b, f, nullptr, d2, dz, nullptr));
+    if (!vel_d2) return BMQ_OK;
     BMQ_CK(cudaMemcpyAsync(s->h_red, s->d_red, 5 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     BMQ_CK(cudaStreamSynchronize(s->stream));
     *vel_d2 = s->h_red[1];
@@ -986,7 +991,7 @@ enum { MG_NARROW = 5, MG_EVENTS = 32 };
 
 struct MgGroup { const int *ids; int n; int width; };
 
-struct MgBlobHeader { long long pid; int n_allocs; int halo; int rank; int pad; };
+struct MgBlobHeader { long long pid; int n_allocs; int halo; int rank; int pad; unsigned char sig_ipc[64]; void *sig_raw; };
 struct MgBlobEntry { unsigned char ipc[64]; void *raw; };
 
 int mg_slab_k0(int nk, int world, int r) { const int base = nk / world, rem = nk % world; return r * base + (r < rem ? r : rem); }
@@ -1007,7 +1012,15 @@ struct bmq3d_mg {
     float disp[2] = {0.f, 0.f}, disp_prev[2] = {0.f, 0.f};
     int reinit_count[2] = {0, 0};
     int wv = 3, ws = 3;
+    int chi_valid[2] = {0, 0};                  // halo planes of the backward maps that are up to date, per mapper
     bmq3d_mg_stats stats;
+    // device-side signalling (mg_signal.h): this rank's block, the peers' blocks mapped here, counters
+    int signal_request = BMQ_MG_SIGNAL_AUTO, signal_mode = BMQ_MG_SIGNAL_HOST;
+    MgSignal *sig = nullptr;
+    std::vector<MgSignal *> peer_sig;           // [rank]
+    MgWaitList near_ranks = {}, other_ranks = {};   // ranks within halo reach (exchange barrier) / all other ranks (reductions)
+    unsigned epoch = 0, red_seq = 0;
+    float *red_host = nullptr;                  // pinned: MG_RED_MAX results + the timed-out flag
 };
 
 namespace {
@@ -1024,15 +1037,30 @@ void mg_owned(const bmq3d_mg *m, int dz, int r, int &a, int &b)
 
 // Posts one exchange on the copy stream: wait for this rank's producers, barrier, pull every halo segment
 // out of its owner's memory.  Returns the event the consumers wait for.
+// Two implementations of barrier + pull (bmq3d_mg_set_signalling):
+//   host callbacks:  the host's stream barrier (an all-rank collective), then one cudaMemcpyAsync per segment;
+//   device flags:    ONE kernel that publishes this rank's arrival, waits for the ranks within halo reach and
+//                    copies all segments with 128-bit loads over NVLink (mg_signal.cu); BMQ_MG_SIGNAL_DEVICE_CE
+//                    keeps the flag barrier but leaves the copies to the copy engines.
 int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, cudaEvent_t *done)
 {
     bmq3d_solver *s = m->s;
     cudaEvent_t produced = mg_event(m);
     BMQ_CK(cudaEventRecord(produced, s->stream));
     BMQ_CK(cudaStreamWaitEvent(m->copy, produced, 0));
-    if (m->world > 1) {
+    const bool flags = m->world > 1 && m->signal_mode != BMQ_MG_SIGNAL_HOST;
+    const bool by_kernel = m->signal_mode == BMQ_MG_SIGNAL_DEVICE;
+    if (m->world > 1 && !flags) {
         if (!m->barrier) return set_error(BMQ_ERR_ARG, "bmq3d_mg: no stream barrier callback set");
         if (m->barrier((void *)m->copy, m->ctx) != 0) return set_error(BMQ_ERR_CUDA, "bmq3d_mg: the stream barrier callback failed");
+    }
+    MgSegList segs;
+    segs.n = 0;
+    unsigned epoch = flags ? ++m->epoch : 0u;
+    if (flags && !by_kernel) {
+        segs.n = 0;
+        BMQ_CK(launch_mg_pull(m->copy, m->sig, m->near_ranks, epoch, segs));      // barrier only
+        epoch = 0;
     }
     for (int g = 0; g < ngroups; ++g) {
         for (int q = 0; q < groups[g].n; ++q) {
@@ -1055,12 +1083,23 @@ int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, cudaEvent_t *done)
                     const int q0 = k0r - s->halo > 0 ? k0r - s->halo : 0;     // first plane rank r stores (same halo everywhere)
                     const char *src = (const char *)m->peer[r][fd->alloc_id] + sizeof(float) * fd->plane() * (size_t)(a - q0);
                     char *dst = (char *)fd->alloc + sizeof(float) * fd->plane() * (size_t)(a - fd->p0);
-                    BMQ_CK(cudaMemcpyAsync(dst, src, sizeof(float) * fd->plane() * (size_t)(b - a), cudaMemcpyDefault, m->copy));
-                    m->stats.bytes_exchanged += (long long)(sizeof(float) * fd->plane() * (size_t)(b - a));
+                    const size_t bytes = sizeof(float) * fd->plane() * (size_t)(b - a);
+                    if (by_kernel) {
+                        if (segs.n == MG_MAX_SEG) {
+                            BMQ_CK(launch_mg_pull(m->copy, m->sig, m->near_ranks, epoch, segs));
+                            epoch = 0;
+                            segs.n = 0;
+                        }
+                        segs.seg[segs.n++] = MgSeg{src, dst, (unsigned long long)bytes};
+                    } else {
+                        BMQ_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, m->copy));
+                    }
+                    m->stats.bytes_exchanged += (long long)bytes;
                 }
             }
         }
     }
+    if (by_kernel && (segs.n > 0 || epoch)) BMQ_CK(launch_mg_pull(m->copy, m->sig, m->near_ranks, epoch, segs));
     *done = mg_event(m);
     BMQ_CK(cudaEventRecord(*done, m->copy));
     m->stats.exchanges++;
@@ -1074,9 +1113,19 @@ int mg_exchange(bmq3d_mg *m, const MgGroup *groups, int ngroups)
     return mg_wait(m, done);
 }
 
-int mg_reduce(bmq3d_mg *m, float *vals, int n)
+// dev_vals != nullptr (device-flag signalling only): this rank's contribution is still on the device, `vals` receives the maxima
+int mg_reduce(bmq3d_mg *m, float *vals, int n, const float *dev_vals = nullptr)
 {
     if (m->world == 1) return BMQ_OK;
+    if (m->signal_mode != BMQ_MG_SIGNAL_HOST) {
+        // mailbox reduction over peer memory (mg_signal.cu): one one-warp kernel and one stream synchronisation
+        if (n > MG_RED_MAX) return set_error(BMQ_ERR_ARG, "bmq3d_mg: reduction of %d values", n);
+        BMQ_CK(launch_mg_allreduce_max(m->s->stream, m->sig, m->other_ranks, vals, dev_vals, n, ++m->red_seq, m->red_host));
+        BMQ_CK(cudaStreamSynchronize(m->s->stream));
+        if (m->red_host[MG_RED_MAX] != 0.f) return set_error(BMQ_ERR_CUDA, "bmq3d_mg: a peer did not answer within 30 s (rank %d)", m->rank);
+        for (int q = 0; q < n; ++q) vals[q] = m->red_host[q];
+        return BMQ_OK;
+    }
     if (!m->allreduce) return set_error(BMQ_ERR_ARG, "bmq3d_mg: no all-reduce callback set");
     if (m->allreduce(vals, n, m->ctx) != 0) return set_error(BMQ_ERR_CUDA, "bmq3d_mg: the all-reduce callback failed");
     return BMQ_OK;
@@ -1096,12 +1145,17 @@ const int kBwdpV[3] = {BMQ_F_VBWDP_X, BMQ_F_VBWDP_Y, BMQ_F_VBWDP_Z}, kBwdpS[3] =
 void mg_unmap(bmq3d_mg *m)
 {
     for (int r = 0; r < (int)m->peer.size(); ++r) {
-        if (r < (int)m->peer_is_ipc.size() && m->peer_is_ipc[r])
+        if (r < (int)m->peer_is_ipc.size() && m->peer_is_ipc[r]) {
             for (void *p : m->peer[r]) if (p) cudaIpcCloseMemHandle(p);
+            if (r < (int)m->peer_sig.size() && m->peer_sig[r]) cudaIpcCloseMemHandle(m->peer_sig[r]);
+        }
         m->peer[r].clear();
     }
     m->peer.clear();
+    m->peer_sig.clear();
     m->peer_is_ipc.clear();
+    m->near_ranks.n = m->other_ranks.n = 0;
+    m->signal_mode = BMQ_MG_SIGNAL_HOST;
 }
 
 }  // namespace
@@ -1120,7 +1174,19 @@ int bmq3d_mg_create(int ni, int nj, int nk, float h, float blend_coeff, int rank
     memset(&m->stats, 0, sizeof m->stats);
     if (halo > nk) halo = nk;
     int st = bmq3d_create_slab(ni, nj, nk, h, blend_coeff, mg_slab_k0(nk, world, rank), mg_slab_k0(nk, world, rank + 1), world > 1 ? halo : 0, &m->s);
-    if (st == BMQ_OK) st = check_cuda(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__);
+    if (st == BMQ_OK) {
+        // the exchange kernels go first whenever an SM has room: a posted halo must not queue behind the
+        // thousands of CTAs of the gather kernel it overlaps
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        st = check_cuda(cudaStreamCreateWithPriority(&m->copy, cudaStreamNonBlocking, hi), "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    if (st == BMQ_OK && world > MG_MAX_WORLD) st = set_error(BMQ_ERR_ARG, "bmq3d_mg_create: at most %d ranks", (int)MG_MAX_WORLD);
+    // its own 2 MB allocation: a CUDA IPC handle names a whole allocation, and a block shared with other small
+    // buffers could not be opened a second time by a peer
+    if (st == BMQ_OK) st = check_cuda(cudaMalloc(&m->sig, 2u << 20), "cudaMalloc", __FILE__, __LINE__);
+    if (st == BMQ_OK) st = check_cuda(cudaMemset(m->sig, 0, 2u << 20), "cudaMemset", __FILE__, __LINE__);
+    if (st == BMQ_OK) st = check_cuda(cudaHostAlloc(&m->red_host, (MG_RED_MAX + 4) * sizeof(float), cudaHostAllocDefault), "cudaHostAlloc", __FILE__, __LINE__);
     for (int e = 0; e < MG_EVENTS && st == BMQ_OK; ++e)
         st = check_cuda(cudaEventCreateWithFlags(&m->ev[e], cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
     if (st != BMQ_OK) { bmq3d_mg_destroy(m); return st; }
@@ -1136,6 +1202,8 @@ int bmq3d_mg_destroy(bmq3d_mg *m)
     mg_unmap(m);
     for (auto e : m->ev) if (e) cudaEventDestroy(e);
     if (m->copy) cudaStreamDestroy(m->copy);
+    if (m->sig) cudaFree(m->sig);
+    if (m->red_host) cudaFreeHost(m->red_host);
     if (m->s) bmq3d_destroy(m->s);
     delete m;
     return BMQ_OK;
@@ -1166,7 +1234,12 @@ int bmq3d_mg_export(bmq3d_mg *m, void *blob)
 {
     if (!m || !blob) return set_error(BMQ_ERR_ARG, "bmq3d_mg_export: null argument");
     bmq3d_solver *s = m->s;
-    MgBlobHeader hd{(long long)getpid(), s->n_allocs, s->halo, m->rank, 0};
+    MgBlobHeader hd{(long long)getpid(), s->n_allocs, s->halo, m->rank, 0, {0}, m->sig};
+    {
+        cudaIpcMemHandle_t hnd;
+        BMQ_CK(cudaIpcGetMemHandle(&hnd, m->sig));
+        memcpy(hd.sig_ipc, &hnd, 64);
+    }
     memcpy(blob, &hd, sizeof hd);
     MgBlobEntry *ent = reinterpret_cast<MgBlobEntry *>((char *)blob + sizeof hd);
     memset(ent, 0, sizeof(MgBlobEntry) * (size_t)s->n_allocs);
@@ -1200,7 +1273,9 @@ int bmq3d_mg_connect(bmq3d_mg *m, const void *all_blobs)
     RET_IF(bmq3d_mg_export_size(m, &one));
     mg_unmap(m);
     m->peer.assign(m->world, std::vector<void *>());
+    m->peer_sig.assign(m->world, nullptr);
     m->peer_is_ipc.assign(m->world, 0);
+    bool any_same_process = false;
     for (int r = 0; r < m->world; ++r) {
         if (r == m->rank) continue;
         const char *blob = (const char *)all_blobs + one * (size_t)r;
@@ -1212,6 +1287,15 @@ int bmq3d_mg_connect(bmq3d_mg *m, const void *all_blobs)
         m->peer[r].assign(hd.n_allocs, nullptr);
         const bool same_process = hd.pid == (long long)getpid();
         m->peer_is_ipc[r] = same_process ? 0 : 1;
+        any_same_process |= same_process;
+        if (same_process) m->peer_sig[r] = static_cast<MgSignal *>(hd.sig_raw);
+        else {
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, hd.sig_ipc, 64);
+            void *p = nullptr;
+            BMQ_CK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+            m->peer_sig[r] = static_cast<MgSignal *>(p);
+        }
         for (int a = 0; a < hd.n_allocs; ++a) {
             if (!ent[a].raw) continue;
             if (same_process) { m->peer[r][a] = ent[a].raw; continue; }
@@ -1220,6 +1304,37 @@ int bmq3d_mg_connect(bmq3d_mg *m, const void *all_blobs)
             BMQ_CK(cudaIpcOpenMemHandle(&m->peer[r][a], hnd, cudaIpcMemLazyEnablePeerAccess));
         }
     }
+    // who takes part in this rank's exchange barrier: every rank whose slab lies within the allocated halo of
+    // this one (either may then pull from the other, whatever width an exchange uses); reductions involve everybody
+    m->near_ranks.n = m->other_ranks.n = 0;
+    for (int r = 0; r < m->world; ++r) {
+        if (r == m->rank) continue;
+        m->other_ranks.sig[m->other_ranks.n++] = m->peer_sig[r];
+        const int gap = r > m->rank ? mg_slab_k0(m->s->nk, m->world, r) - m->s->k1 : m->s->k0 - mg_slab_k0(m->s->nk, m->world, r + 1);
+        if (gap < m->s->halo + 2) m->near_ranks.sig[m->near_ranks.n++] = m->peer_sig[r];
+    }
+    // device-side signalling spins in kernels: the default for one process per GPU; ranks that share a process
+    // (and possibly a GPU, where a spinning kernel could keep its peer's kernel from running) stay with the callbacks
+    int mode = m->signal_request;
+    if (mode == BMQ_MG_SIGNAL_AUTO) {
+        // measured at 8 GPUs, 512^3: flags + copy engines 11.97 ms per step, flags + pull kernel 12.60 (its CTAs take SM
+        // time from the stages they overlap), host collectives 12.40 (profiles/r2_scaling.md)
+        mode = any_same_process ? BMQ_MG_SIGNAL_HOST : BMQ_MG_SIGNAL_DEVICE_CE;
+        if (const char *e = getenv("BMQ_MG_SIGNAL")) mode = atoi(e);
+    }
+    if (mode != BMQ_MG_SIGNAL_HOST && mode != BMQ_MG_SIGNAL_DEVICE && mode != BMQ_MG_SIGNAL_DEVICE_CE)
+        return set_error(BMQ_ERR_ARG, "bmq3d_mg_connect: unknown signalling mode %d", mode);
+    m->signal_mode = mode;
+    m->stats.signalling = mode;
+    return BMQ_OK;
+}
+
+int bmq3d_mg_set_signalling(bmq3d_mg *m, int mode)
+{
+    if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_set_signalling: null handle");
+    if (mode < BMQ_MG_SIGNAL_AUTO || mode > BMQ_MG_SIGNAL_DEVICE_CE) return set_error(BMQ_ERR_ARG, "bmq3d_mg_set_signalling: unknown mode %d", mode);
+    if (!m->peer.empty()) return set_error(BMQ_ERR_ARG, "bmq3d_mg_set_signalling: call it before bmq3d_mg_connect (every rank the same mode)");
+    m->signal_request = mode;
     return BMQ_OK;
 }
 
@@ -1243,8 +1358,14 @@ int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
     bmq3d_solver *s = m->s;
     if (m->world > 1 && m->peer.empty()) return set_error(BMQ_ERR_ARG, "bmq3d_mg_advect: not connected");
     float gmax = 0.f;
-    RET_IF(stage_maxvel(s, &gmax));
-    RET_IF(mg_reduce(m, &gmax, 1));
+    const bool on_device = m->world > 1 && m->signal_mode != BMQ_MG_SIGNAL_HOST;   // reductions without a host round trip in between
+    if (on_device) {
+        RET_IF(stage_maxvel(s, nullptr));
+        RET_IF(mg_reduce(m, &gmax, 1, s->d_red));
+    } else {
+        RET_IF(stage_maxvel(s, &gmax));
+        RET_IF(mg_reduce(m, &gmax, 1));
+    }
     set_cfl(s, framenum, gmax);
     const float cfl_frame = dt * (gmax > 1e-4f ? gmax : 1e-4f) / s->h;
     int need[2], need_b[2] = {0, 0}, widest = MG_NARROW;
@@ -1266,7 +1387,14 @@ int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
     }
     cudaEvent_t h_init, h_bwd = nullptr, h_fwd, h_av, h_as, h_ev, h_es;
     { const MgGroup g[1] = {{kVel, 3, wmax}}; RET_IF(mg_exchange(m, g, 1)); }                       // consumers: DMC, forward
-    { const MgGroup g[2] = {{kBwdV, 3, MG_NARROW}, {kBwdS, 3, MG_NARROW}}; RET_IF(mg_exchange(m, g, 2)); }
+    {   // the DMC sub-step reads 5 planes of chi past the slab; they are still there from the last step's wide exchange
+        // (or from the identity fill of a re-initialisation) unless that step needed fewer than 5
+        MgGroup g[2];
+        int ng = 0;
+        if (m->chi_valid[0] < MG_NARROW) g[ng++] = MgGroup{kBwdV, 3, MG_NARROW};
+        if (m->chi_valid[1] < MG_NARROW) g[ng++] = MgGroup{kBwdS, 3, MG_NARROW};
+        if (ng) RET_IF(mg_exchange(m, g, ng));
+    }
     { const MgGroup g[2] = {{kInitV, 3, wv}, {kInitS, 2, ws}}; RET_IF(mg_post(m, g, 2, &h_init)); }   // overlaps DMC + forward
     float T = 0.f, substep = s->cfldt;
     int n = 0;
@@ -1276,7 +1404,11 @@ int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
         T += substep;
         if (++n > 4096) return set_error(BMQ_ERR_ARG, "bmq3d_mg_advect: more than 4096 CFL sub-steps");
         if (T < dt) { const MgGroup g[2] = {{kBwdV, 3, MG_NARROW}, {kBwdS, 3, MG_NARROW}}; RET_IF(mg_exchange(m, g, 2)); }
-        else { const MgGroup g[2] = {{kBwdV, 3, wv}, {kBwdS, 3, ws}}; RET_IF(mg_post(m, g, 2, &h_bwd)); }   // overlaps forward
+        else {
+            const MgGroup g[2] = {{kBwdV, 3, wv}, {kBwdS, 3, ws}};
+            RET_IF(mg_post(m, g, 2, &h_bwd));                                                        // overlaps forward
+            m->chi_valid[0] = wv; m->chi_valid[1] = ws;
+        }
     }
     s->stats.n_substeps = n;
     RET_IF(stage_forward(s, dt));
@@ -1318,8 +1450,14 @@ int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt)
         RET_IF(mg_post(m, g, 2, &h_ch));                                                             // overlaps the distortion kernel
     }
     float red[4] = {0, 0, 0, 0};
-    RET_IF(stage_distortion(s, &red[0], &red[1], &red[2]));     // red[2], red[3] = z displacement per mapper
-    RET_IF(mg_reduce(m, red, 4));
+    if (m->world > 1 && m->signal_mode != BMQ_MG_SIGNAL_HOST) {
+        RET_IF(stage_distortion(s, nullptr, nullptr, nullptr));
+        RET_IF(mg_reduce(m, red, 4, s->d_red + 1));
+        red[2] /= s->h; red[3] /= s->h;                         // as stage_distortion reports them: in cells
+    } else {
+        RET_IF(stage_distortion(s, &red[0], &red[1], &red[2]));     // red[2], red[3] = z displacement per mapper
+        RET_IF(mg_reduce(m, red, 4));
+    }
     m->disp[0] = red[2]; m->disp[1] = red[3];
     s->stats.max_disp_z_vel = red[2]; s->stats.max_disp_z_scalar = red[3];
     s->stats.max_disp_z = red[2] > red[3] ? red[2] : red[3];
@@ -1332,11 +1470,13 @@ int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt)
         RET_IF(stage_reinit(s, 0, 1));
         m->reinit_count[0]++;
         m->disp_prev[0] = m->disp[0]; m->disp[0] = 0.f;
+        m->chi_valid[0] = s->halo;                               // the identity fill covers every stored plane
     }
     if (s->scalar_reinit) {
         RET_IF(stage_reinit(s, 1, 0));
         m->reinit_count[1]++;
         m->disp_prev[1] = m->disp[1]; m->disp[1] = 0.f;
+        m->chi_valid[1] = s->halo;
     }
     s->stats.vel_reinit_count = s->vel_reinit_count;
     s->stats.scalar_reinit_count = s->scalar_reinit_count;

@@ -681,7 +681,9 @@ class _NativeStepper:
         self.slab.advect(frame, dt)
         st = self.slab.mg_stats()
         self.stats.update(halo_used=max(st["halo_vel"], st["halo_scalar"]), halo_vel=st["halo_vel"], halo_scalar=st["halo_scalar"],
-                          halo_allocated=st["halo_allocated"], n_substeps=self.slab.solver.stats()["n_substeps"])
+                          halo_allocated=st["halo_allocated"], n_substeps=self.slab.solver.stats()["n_substeps"],
+                          signalling={0: "host callbacks + copy engines", 1: "device flags + pull kernel",
+                                      2: "device flags + copy engines"}.get(st["signalling"], st["signalling"]))
 
     def accumulate(self, frame, dt):
         self.slab.accumulate(frame, dt)

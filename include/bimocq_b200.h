@@ -378,11 +378,24 @@ typedef struct bmq3d_mg_stats {
     int halo_allocated, halo_needed, halo_vel, halo_scalar;   /* planes: allocated; widest needed; exchanged last step per mapper */
     int halo_grown;                                           /* number of bmq3d_mg_grow_halo calls */
     long long exchanges, bytes_exchanged;                     /* since creation */
+    int signalling;                                           /* BMQ_MG_SIGNAL_* in effect since the last connect */
 } bmq3d_mg_stats;
+/* How the ranks synchronise a halo exchange and reduce their maxima.
+ *   HOST       the two callbacks of bmq3d_mg_set_collectives (an all-rank stream barrier per exchange, a blocking
+ *              all-reduce) and one cudaMemcpyAsync per halo segment;
+ *   DEVICE     no callbacks: every rank owns a block of flags in device memory that its peers map; an exchange is
+ *              ONE kernel that publishes the rank's arrival, waits for the ranks within halo reach and pulls all
+ *              segments over NVLink with 128-bit loads; reductions go through per-rank mailboxes (csrc/mg_signal.h);
+ *   DEVICE_CE  the flag barrier of DEVICE, copies by the copy engines (cudaMemcpyAsync);
+ *   AUTO       (default) DEVICE when every peer is another process (one process per GPU), HOST when ranks share
+ *              a process; the environment variable BMQ_MG_SIGNAL = 0 / 1 / 2 overrides AUTO.
+ * Every rank must use the same mode; set it before bmq3d_mg_connect. */
+enum { BMQ_MG_SIGNAL_AUTO = -1, BMQ_MG_SIGNAL_HOST = 0, BMQ_MG_SIGNAL_DEVICE = 1, BMQ_MG_SIGNAL_DEVICE_CE = 2 };
 int bmq3d_mg_create(int ni, int nj, int nk, float h, float blend_coeff, int rank, int world, int halo, bmq3d_mg **out);
 int bmq3d_mg_destroy(bmq3d_mg *m);
 int bmq3d_mg_solver(bmq3d_mg *m, bmq3d_solver **out);        /* the rank's slab handle (owned by m) */
 int bmq3d_mg_set_collectives(bmq3d_mg *m, bmq_allreduce_max_fn allreduce_max, bmq_stream_barrier_fn stream_barrier, void *ctx);
+int bmq3d_mg_set_signalling(bmq3d_mg *m, int mode);          /* BMQ_MG_SIGNAL_*; before bmq3d_mg_connect */
 int bmq3d_mg_export_size(bmq3d_mg *m, size_t *bytes);
 int bmq3d_mg_export(bmq3d_mg *m, void *blob);
 int bmq3d_mg_connect(bmq3d_mg *m, const void *all_blobs);    /* world blobs of bmq3d_mg_export_size bytes, in rank order */

@@ -22,16 +22,23 @@ def main():
     dev = torch.device("cuda", local)
     u, v, w, rho, T = scenes.smoke_plume(ni, nj, nk, 1.0, xp=torch, device=dev)
     u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
-    for transport in ("native", "peer", "nccl"):
-        run(transport, rank, world, ni, nj, nk, h, halo, frames, dt, u, v, w, rho, T)
+    # the C-level driver with its three ways of synchronising an exchange (device flags + pull kernel, device flags +
+    # copy engines, the host's collectives), then the two Python transports
+    for transport, signal in (("native", 1), ("native", 2), ("native", 0), ("peer", None), ("nccl", None)):
+        if signal is not None:
+            os.environ["BMQ_MG_SIGNAL"] = str(signal)
+        run(transport, rank, world, ni, nj, nk, h, halo, frames, dt, u, v, w, rho, T, signal)
     dist.barrier()
     if rank == 0:
         print("ZSLAB_NCCL_OK", world, "ranks")
     dist.destroy_process_group()
 
 
-def run(transport, rank, world, ni, nj, nk, h, halo, frames, dt, u, v, w, rho, T):
+def run(transport, rank, world, ni, nj, nk, h, halo, frames, dt, u, v, w, rho, T, signal=None):
     z = zslab.ZSlabAdvection3D(ni, nj, nk, h, 1.0, rank=rank, world=world, halo=halo, transport=transport)
+    if signal is not None:
+        assert z.r.mg_stats()["signalling"] == signal, z.r.mg_stats()
+        transport = f"native/signal={signal}"
     z.set_initial_device(u, v, w, rho, T)
     single = BimocqAdvection3D(ni, nj, nk, h, 1.0)
     single.set_initial_device(u, v, w, rho, T)
