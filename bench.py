@@ -258,7 +258,8 @@ def timed_steps(solver, torch, dist, world, dev, steps, warmup, beta=1e-2, on_ti
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    stage = solver.timing_read()
+    # (ms, spans, ms the compute stream idled before the stage: halo exchanges, reductions, host round trips)
+    stage = solver.timing_read_gaps() if hasattr(solver, "timing_read_gaps") else solver.timing_read()
     solver.timing_enable(False)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -361,6 +362,14 @@ def run_gpu(args):
                                "achieved_gbs": whole_gbs, "peak_gbs": peak * world, "frac": whole_gbs / (peak * world)},
                 "stage_ms_per_step": {k: round(v / args.steps, 4) for k, v in shares.items()}}
 
+    # every rank's own kernel time and idle time: the step runs at the pace of the slowest slab (data-dependent: gathers
+    # in the plume's slabs miss L1 more often than gathers through near-identity maps in still air)
+    per_rank = None
+    if world > 1:
+        mine = {"stage_kernels_ms_per_step": round(total_stage_ms / args.steps, 4),
+                "idle_ms_per_step": round(sum(v[2] for v in stage.values() if len(v) > 2) / args.steps, 4)}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     line = None
     if rank == 0:
         par = "single GPU"
@@ -380,6 +389,16 @@ def run_gpu(args):
                                     if n >= 512 else f"{4 * n ** 3 / 1e6:.0f} MB per field, ~60 fields: working set larger than the 126 MB L2"},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         }
+        if world > 1:
+            # rank 0's view of where the step's fixed cost sits: time its compute stream idled before each stage
+            waits = {k: round(v[2] / args.steps, 4) for k, v in stage.items() if len(v) > 2 and v[1] > 0 and v[2] / args.steps >= 0.005}
+            line["multi_gpu"] = {"stage_kernels_ms_per_step": round(total_stage_ms / args.steps, 4),
+                                 "fixed_cost_ms_per_step": round(ms_per_step - total_stage_ms / args.steps, 4),
+                                 "idle_before_stage_ms_per_step": dict(sorted(waits.items(), key=lambda kv: -kv[1])),
+                                 "per_rank_stage_kernels_ms_per_step": [r["stage_kernels_ms_per_step"] for r in per_rank],
+                                 "per_rank_idle_ms_per_step": [r["idle_ms_per_step"] for r in per_rank],
+                                 "note": "idle time before a stage = the halo exchange / reduction / host round trip it waited for "
+                                         "(distortion also waits for the caller's buoyancy kernel)"}
 
     # ---- e2e: the same metric through the C-ABI host-buffer calls (pinned host memory, copies timed)
     if world > 1 and not args.no_e2e:

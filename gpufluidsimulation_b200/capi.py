@@ -172,6 +172,7 @@ _PROTOS = {
     "bmq3d_get_stats": (_I, [_H, C.POINTER(Stats3D)]),
     "bmq3d_timing_enable": (_I, [_H, _I]),
     "bmq3d_timing_read": (_I, [_H, _F, C.POINTER(_I), _I]),
+    "bmq3d_timing_read_gaps": (_I, [_H, _F, C.POINTER(_I), _F, _I]),
     "bmq3d_timing_slot_name": (C.c_char_p, [_I]),
     "bmq3d_advect_host": (_I, [_H, _I, _f] + [C.c_void_p] * 5),
     "bmq3d_accumulate_host": (_I, [_H, _I, _f] + [C.c_void_p] * 8),

@@ -807,6 +807,23 @@ int bmq3d_timing_read(bmq3d_solver *s, float *ms_out, int *spans_out, int n_slot
     return BMQ_OK;
 }
 
+// As bmq3d_timing_read, plus per slot the time the stream spent between the end of the previous recorded stage and
+// the start of this one: what a stage waited for (a halo exchange, a reduction with its host round trip, the
+// caller's own kernels) -- the fixed cost of the z-slab step, named by the stage that had to wait.
+int bmq3d_timing_read_gaps(bmq3d_solver *s, float *ms_out, int *spans_out, float *gap_ms_out, int n_slots)
+{
+    NEED(s);
+    if (!ms_out || !gap_ms_out || n_slots < BMQ_T_COUNT) return set_error(BMQ_ERR_ARG, "bmq3d_timing_read_gaps: need %d slots", (int)BMQ_T_COUNT);
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    for (int q = 0; q < n_slots; ++q) gap_ms_out[q] = 0.f;
+    for (size_t i = 1; i < s->spans.size(); ++i) {
+        float ms = 0.f;
+        BMQ_CK(cudaEventElapsedTime(&ms, s->spans[i - 1].b, s->spans[i].a));
+        gap_ms_out[s->spans[i].slot] += ms;
+    }
+    return bmq3d_timing_read(s, ms_out, spans_out, n_slots);
+}
+
 int bmq3d_get_stats(bmq3d_solver *s, bmq3d_stats *out)
 {
     NEED(s);
@@ -988,6 +1005,9 @@ static int accumulate_host_impl(bmq3d_solver *s, int framenum, float dt, const f
 namespace {
 
 enum { MG_NARROW = 5, MG_EVENTS = 32 };
+// posted exchanges whose completion is waited for later in the step, each with its own event
+enum MgDone { MG_D_BLOCKING = 0, MG_D_VEL, MG_D_INIT, MG_D_BWD, MG_D_FWD, MG_D_ADV_V, MG_D_ADV_S, MG_D_ERR_V, MG_D_ERR_S, MG_D_CH_V, MG_D_CH_S,
+              MG_DONE_EVENTS };
 
 struct MgGroup { const int *ids; int n; int width; };
 
@@ -1001,9 +1021,10 @@ int mg_slab_k0(int nk, int world, int r) { const int base = nk / world, rem = nk
 struct bmq3d_mg {
     bmq3d_solver *s = nullptr;
     int rank = 0, world = 1;
-    cudaStream_t copy = nullptr;
-    cudaEvent_t ev[MG_EVENTS] = {};
+    cudaStream_t copy = nullptr, copy2 = nullptr;   // copy: barrier + pulls from the lower side; copy2: pulls from the upper side
+    cudaEvent_t ev[MG_EVENTS] = {};                 // transient events (waited for right after they are recorded)
     int ev_next = 0;
+    cudaEvent_t done_ev[MG_DONE_EVENTS] = {};       // completion of the posted exchanges, one per purpose (see MgDone)
     std::vector<std::vector<void *>> peer;      // [rank][alloc_id]: base of that rank's allocation, mapped here
     std::vector<char> peer_is_ipc;              // [rank]: mapped with cudaIpcOpenMemHandle (must be closed)
     bmq_allreduce_max_fn allreduce = nullptr;
@@ -1042,7 +1063,7 @@ void mg_owned(const bmq3d_mg *m, int dz, int r, int &a, int &b)
 //   device flags:    ONE kernel that publishes this rank's arrival, waits for the ranks within halo reach and
 //                    copies all segments with 128-bit loads over NVLink (mg_signal.cu); BMQ_MG_SIGNAL_DEVICE_CE
 //                    keeps the flag barrier but leaves the copies to the copy engines.
-int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, cudaEvent_t *done)
+int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, MgDone which)
 {
     bmq3d_solver *s = m->s;
     cudaEvent_t produced = mg_event(m);
@@ -1061,6 +1082,14 @@ int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, cudaEvent_t *done)
         segs.n = 0;
         BMQ_CK(launch_mg_pull(m->copy, m->sig, m->near_ranks, epoch, segs));      // barrier only
         epoch = 0;
+    }
+    // copy engines: the two sides of the slab are pulled by two streams, so two engines (and both directions of the
+    // links) work at once; the upper side starts after the barrier and joins before the exchange is complete
+    const bool two_streams = m->world > 1 && !by_kernel;
+    if (two_streams) {
+        cudaEvent_t open = mg_event(m);
+        BMQ_CK(cudaEventRecord(open, m->copy));
+        BMQ_CK(cudaStreamWaitEvent(m->copy2, open, 0));
     }
     for (int g = 0; g < ngroups; ++g) {
         for (int q = 0; q < groups[g].n; ++q) {
@@ -1092,7 +1121,7 @@ int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, cudaEvent_t *done)
                         }
                         segs.seg[segs.n++] = MgSeg{src, dst, (unsigned long long)bytes};
                     } else {
-                        BMQ_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, m->copy));
+                        BMQ_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, side && two_streams ? m->copy2 : m->copy));
                     }
                     m->stats.bytes_exchanged += (long long)bytes;
                 }
@@ -1100,17 +1129,20 @@ int mg_post(bmq3d_mg *m, const MgGroup *groups, int ngroups, cudaEvent_t *done)
         }
     }
     if (by_kernel && (segs.n > 0 || epoch)) BMQ_CK(launch_mg_pull(m->copy, m->sig, m->near_ranks, epoch, segs));
-    *done = mg_event(m);
-    BMQ_CK(cudaEventRecord(*done, m->copy));
+    if (two_streams) {
+        cudaEvent_t upper = mg_event(m);
+        BMQ_CK(cudaEventRecord(upper, m->copy2));
+        BMQ_CK(cudaStreamWaitEvent(m->copy, upper, 0));
+    }
+    BMQ_CK(cudaEventRecord(m->done_ev[which], m->copy));
     m->stats.exchanges++;
     return BMQ_OK;
 }
-int mg_wait(bmq3d_mg *m, cudaEvent_t done) { BMQ_CK(cudaStreamWaitEvent(m->s->stream, done, 0)); return BMQ_OK; }
+int mg_wait(bmq3d_mg *m, MgDone which) { BMQ_CK(cudaStreamWaitEvent(m->s->stream, m->done_ev[which], 0)); return BMQ_OK; }
 int mg_exchange(bmq3d_mg *m, const MgGroup *groups, int ngroups)
 {
-    cudaEvent_t done;
-    RET_IF(mg_post(m, groups, ngroups, &done));
-    return mg_wait(m, done);
+    RET_IF(mg_post(m, groups, ngroups, MG_D_BLOCKING));
+    return mg_wait(m, MG_D_BLOCKING);
 }
 
 // dev_vals != nullptr (device-flag signalling only): this rank's contribution is still on the device, `vals` receives the maxima
@@ -1180,6 +1212,7 @@ int bmq3d_mg_create(int ni, int nj, int nk, float h, float blend_coeff, int rank
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         st = check_cuda(cudaStreamCreateWithPriority(&m->copy, cudaStreamNonBlocking, hi), "cudaStreamCreate", __FILE__, __LINE__);
+        if (st == BMQ_OK) st = check_cuda(cudaStreamCreateWithPriority(&m->copy2, cudaStreamNonBlocking, hi), "cudaStreamCreate", __FILE__, __LINE__);
     }
     if (st == BMQ_OK && world > MG_MAX_WORLD) st = set_error(BMQ_ERR_ARG, "bmq3d_mg_create: at most %d ranks", (int)MG_MAX_WORLD);
     // its own 2 MB allocation: a CUDA IPC handle names a whole allocation, and a block shared with other small
@@ -1189,6 +1222,8 @@ int bmq3d_mg_create(int ni, int nj, int nk, float h, float blend_coeff, int rank
     if (st == BMQ_OK) st = check_cuda(cudaHostAlloc(&m->red_host, (MG_RED_MAX + 4) * sizeof(float), cudaHostAllocDefault), "cudaHostAlloc", __FILE__, __LINE__);
     for (int e = 0; e < MG_EVENTS && st == BMQ_OK; ++e)
         st = check_cuda(cudaEventCreateWithFlags(&m->ev[e], cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
+    for (int e = 0; e < MG_DONE_EVENTS && st == BMQ_OK; ++e)
+        st = check_cuda(cudaEventCreateWithFlags(&m->done_ev[e], cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
     if (st != BMQ_OK) { bmq3d_mg_destroy(m); return st; }
     m->stats.halo_allocated = m->s->halo;
     *out = m;
@@ -1199,9 +1234,12 @@ int bmq3d_mg_destroy(bmq3d_mg *m)
 {
     if (!m) return BMQ_OK;
     if (m->copy) cudaStreamSynchronize(m->copy);
+    if (m->copy2) cudaStreamSynchronize(m->copy2);
     mg_unmap(m);
     for (auto e : m->ev) if (e) cudaEventDestroy(e);
+    for (auto e : m->done_ev) if (e) cudaEventDestroy(e);
     if (m->copy) cudaStreamDestroy(m->copy);
+    if (m->copy2) cudaStreamDestroy(m->copy2);
     if (m->sig) cudaFree(m->sig);
     if (m->red_host) cudaFreeHost(m->red_host);
     if (m->s) bmq3d_destroy(m->s);
@@ -1261,6 +1299,7 @@ int bmq3d_mg_disconnect(bmq3d_mg *m)
 {
     if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_disconnect: null handle");
     BMQ_CK(cudaStreamSynchronize(m->copy));
+    BMQ_CK(cudaStreamSynchronize(m->copy2));
     BMQ_CK(cudaStreamSynchronize(m->s->stream));
     mg_unmap(m);
     return BMQ_OK;
@@ -1359,6 +1398,16 @@ int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
     if (m->world > 1 && m->peer.empty()) return set_error(BMQ_ERR_ARG, "bmq3d_mg_advect: not connected");
     float gmax = 0.f;
     const bool on_device = m->world > 1 && m->signal_mode != BMQ_MG_SIGNAL_HOST;   // reductions without a host round trip in between
+    // The velocity halo (read by the DMC and the forward trace) does not have to wait for the max-velocity reduction
+    // that sizes it: post it now with last step's width plus two planes, top it up afterwards in the rare case that
+    // the true width is larger.  It then travels while the reduction makes its host round trip.
+    int w_guess = 0;
+    if (m->world > 1) {
+        w_guess = (m->wv > m->ws ? m->wv : m->ws) + 2;
+        if (w_guess > s->halo) w_guess = s->halo;
+        const MgGroup g[1] = {{kVel, 3, w_guess}};
+        RET_IF(mg_post(m, g, 1, MG_D_VEL));
+    }
     if (on_device) {
         RET_IF(stage_maxvel(s, nullptr));
         RET_IF(mg_reduce(m, &gmax, 1, s->d_red));
@@ -1385,8 +1434,8 @@ int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
     if (m->world == 1) {         // a single rank: the plain phase A
         return bmq3d_advect(s, framenum, dt, 0);
     }
-    cudaEvent_t h_init, h_bwd = nullptr, h_fwd, h_av, h_as, h_ev, h_es;
-    { const MgGroup g[1] = {{kVel, 3, wmax}}; RET_IF(mg_exchange(m, g, 1)); }                       // consumers: DMC, forward
+    RET_IF(mg_wait(m, MG_D_VEL));                                                                   // consumers: DMC, forward
+    if (wmax > w_guess) { const MgGroup g[1] = {{kVel, 3, wmax}}; RET_IF(mg_exchange(m, g, 1)); }
     {   // the DMC sub-step reads 5 planes of chi past the slab; they are still there from the last step's wide exchange
         // (or from the identity fill of a re-initialisation) unless that step needed fewer than 5
         MgGroup g[2];
@@ -1395,7 +1444,7 @@ int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
         if (m->chi_valid[1] < MG_NARROW) g[ng++] = MgGroup{kBwdS, 3, MG_NARROW};
         if (ng) RET_IF(mg_exchange(m, g, ng));
     }
-    { const MgGroup g[2] = {{kInitV, 3, wv}, {kInitS, 2, ws}}; RET_IF(mg_post(m, g, 2, &h_init)); }   // overlaps DMC + forward
+    { const MgGroup g[2] = {{kInitV, 3, wv}, {kInitS, 2, ws}}; RET_IF(mg_post(m, g, 2, MG_D_INIT)); }   // overlaps DMC + forward
     float T = 0.f, substep = s->cfldt;
     int n = 0;
     while (T < dt) {
@@ -1406,29 +1455,29 @@ int bmq3d_mg_advect(bmq3d_mg *m, int framenum, float dt)
         if (T < dt) { const MgGroup g[2] = {{kBwdV, 3, MG_NARROW}, {kBwdS, 3, MG_NARROW}}; RET_IF(mg_exchange(m, g, 2)); }
         else {
             const MgGroup g[2] = {{kBwdV, 3, wv}, {kBwdS, 3, ws}};
-            RET_IF(mg_post(m, g, 2, &h_bwd));                                                        // overlaps forward
+            RET_IF(mg_post(m, g, 2, MG_D_BWD));                                                       // overlaps forward
             m->chi_valid[0] = wv; m->chi_valid[1] = ws;
         }
     }
     s->stats.n_substeps = n;
     RET_IF(stage_forward(s, dt));
-    { const MgGroup g[2] = {{kFwdV, 3, wv}, {kFwdS, 3, ws}}; RET_IF(mg_post(m, g, 2, &h_fwd)); }      // overlaps advect
-    if (h_bwd) RET_IF(mg_wait(m, h_bwd));
-    RET_IF(mg_wait(m, h_init));
+    { const MgGroup g[2] = {{kFwdV, 3, wv}, {kFwdS, 3, ws}}; RET_IF(mg_post(m, g, 2, MG_D_FWD)); }      // overlaps advect
+    RET_IF(mg_wait(m, MG_D_BWD));
+    RET_IF(mg_wait(m, MG_D_INIT));
     RET_IF(stage_advect(s, 0));
-    { const MgGroup g[1] = {{kAdvV, 3, wv}}; RET_IF(mg_post(m, g, 1, &h_av)); }
+    { const MgGroup g[1] = {{kAdvV, 3, wv}}; RET_IF(mg_post(m, g, 1, MG_D_ADV_V)); }
     RET_IF(stage_advect(s, 1));
-    { const MgGroup g[1] = {{kAdvS, 2, ws}}; RET_IF(mg_post(m, g, 1, &h_as)); }
-    RET_IF(mg_wait(m, h_fwd));
-    RET_IF(mg_wait(m, h_av));
+    { const MgGroup g[1] = {{kAdvS, 2, ws}}; RET_IF(mg_post(m, g, 1, MG_D_ADV_S)); }
+    RET_IF(mg_wait(m, MG_D_FWD));
+    RET_IF(mg_wait(m, MG_D_ADV_V));
     RET_IF(stage_error(s, 0));
-    { const MgGroup g[1] = {{kErrV, 3, wv}}; RET_IF(mg_post(m, g, 1, &h_ev)); }
-    RET_IF(mg_wait(m, h_as));
+    { const MgGroup g[1] = {{kErrV, 3, wv}}; RET_IF(mg_post(m, g, 1, MG_D_ERR_V)); }
+    RET_IF(mg_wait(m, MG_D_ADV_S));
     RET_IF(stage_error(s, 1));
-    { const MgGroup g[1] = {{kErrS, 2, ws}}; RET_IF(mg_post(m, g, 1, &h_es)); }
-    RET_IF(mg_wait(m, h_ev));
+    { const MgGroup g[1] = {{kErrS, 2, ws}}; RET_IF(mg_post(m, g, 1, MG_D_ERR_S)); }
+    RET_IF(mg_wait(m, MG_D_ERR_V));
     RET_IF(stage_apply(s, 0));
-    RET_IF(mg_wait(m, h_es));
+    RET_IF(mg_wait(m, MG_D_ERR_S));
     RET_IF(stage_apply(s, 1));
     for (int which = 0; which < 2; ++which) {
         if (!blend_on[which]) continue;
@@ -1444,10 +1493,12 @@ int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt)
 {
     if (!m) return set_error(BMQ_ERR_ARG, "bmq3d_mg_accumulate: null handle");
     bmq3d_solver *s = m->s;
-    cudaEvent_t h_ch = nullptr;
     if (m->world > 1) {
-        const MgGroup g[2] = {{kChV, 6, m->wv}, {kChS, 2, m->ws}};
-        RET_IF(mg_post(m, g, 2, &h_ch));                                                             // overlaps the distortion kernel
+        // the scalars' two change fields first, then the velocity's six: the scalar accumulation runs while the larger
+        // exchange is still travelling (both overlap the distortion kernel and its reduction)
+        const MgGroup gs[1] = {{kChS, 2, m->ws}}, gv[1] = {{kChV, 6, m->wv}};
+        RET_IF(mg_post(m, gs, 1, MG_D_CH_S));
+        RET_IF(mg_post(m, gv, 1, MG_D_CH_V));
     }
     float red[4] = {0, 0, 0, 0};
     if (m->world > 1 && m->signal_mode != BMQ_MG_SIGNAL_HOST) {
@@ -1462,9 +1513,10 @@ int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt)
     s->stats.max_disp_z_vel = red[2]; s->stats.max_disp_z_scalar = red[3];
     s->stats.max_disp_z = red[2] > red[3] ? red[2] : red[3];
     decide(s, framenum, dt, red[0], red[1]);
-    if (h_ch) RET_IF(mg_wait(m, h_ch));
+    if (m->world > 1) RET_IF(mg_wait(m, MG_D_CH_S));
+    RET_IF(stage_accumulate(s, 1));         // independent of the velocity's accumulation: any order gives the same fields
+    if (m->world > 1) RET_IF(mg_wait(m, MG_D_CH_V));
     RET_IF(stage_accumulate(s, 0));
-    RET_IF(stage_accumulate(s, 1));
     if (s->vel_reinit) {
         RET_IF(stage_reinit(s, 0, 0));
         RET_IF(stage_reinit(s, 0, 1));

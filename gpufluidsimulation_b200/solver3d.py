@@ -364,6 +364,13 @@ class BimocqAdvection3D:
         check(self.lib.bmq3d_timing_read(self._h, ms, cnt, n), "bmq3d_timing_read")
         return {self.lib.bmq3d_timing_slot_name(q).decode(): (ms[q], cnt[q]) for q in range(n)}
 
+    def timing_read_gaps(self):
+        """{stage name: (milliseconds, spans, milliseconds the stream idled before the stage)} since the last read."""
+        n = capi.N_TIMING_SLOTS
+        ms = (C.c_float * n)(); cnt = (C.c_int * n)(); gap = (C.c_float * n)()
+        check(self.lib.bmq3d_timing_read_gaps(self._h, ms, cnt, gap, n), "bmq3d_timing_read_gaps")
+        return {self.lib.bmq3d_timing_slot_name(q).decode(): (ms[q], cnt[q], gap[q]) for q in range(n)}
+
     # fine-grained stages (z-slab driver)
     def stage(self, name, *args):
         fn = getattr(self.lib, "bmq3d_stage_" + name)

@@ -852,6 +852,9 @@ class ZSlabAdvection3D:
     def timing_read(self):
         return self.r.solver.timing_read()
 
+    def timing_read_gaps(self):
+        return self.r.solver.timing_read_gaps()
+
     def close(self):
         if self.comm is None:                 # native driver: unmap the peers before anybody frees
             self.torch.cuda.synchronize()

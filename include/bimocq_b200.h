@@ -304,6 +304,8 @@ enum { BMQ_T_MAXVEL = 0, BMQ_T_DMC, BMQ_T_FORWARD, BMQ_T_SEMILAG, BMQ_T_ADVECT_V
        BMQ_T_DISTORTION, BMQ_T_ACCUM_V, BMQ_T_ACCUM_S, BMQ_T_REINIT, BMQ_T_COUNT };
 int bmq3d_timing_enable(bmq3d_solver *s, int on);
 int bmq3d_timing_read(bmq3d_solver *s, float *ms_out, int *spans_out, int n_slots);
+/* the same, plus per slot the idle time of the stream before that stage started (what it waited for) */
+int bmq3d_timing_read_gaps(bmq3d_solver *s, float *ms_out, int *spans_out, float *gap_ms_out, int n_slots);
 const char *bmq3d_timing_slot_name(int slot);
 
 /* Whole step through HOST buffers (the reference's host-orchestrated solver keeps its fields on
