@@ -102,12 +102,36 @@ static inline dim3 grid3(int fi, int fj, KRange r)
 {
     return dim3((fi + 31) / 32, (fj + BMQ_BY - 1) / BMQ_BY, (r.kend - r.kbeg + BMQ_BZ - 1) / BMQ_BZ);
 }
+// planes per CTA of the column kernels (BMQ_COLUMN): long enough for L1 reuse along z, short enough that the grid
+// still fills 148 SMs x 8 CTAs a few times over; BMQ_COLUMN_CHUNK overrides (1 = one cell per thread)
+static int column_chunk(int fi, int fj, int nplanes)
+{
+    static const int forced = [] { const char *e = getenv("BMQ_COLUMN_CHUNK"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return forced;
+    const long long cols = (long long)((fi + 31) / 32) * ((fj + BMQ_BY - 1) / BMQ_BY);
+    int kc = 16;
+    while (kc > 1 && cols * ((nplanes + kc - 1) / kc) < 148ll * 8 * 4) kc /= 2;
+    return kc;
+}
+static inline dim3 grid3_columns(int fi, int fj, KRange r, int kc)
+{
+    return dim3((fi + 31) / 32, (fj + BMQ_BY - 1) / BMQ_BY, (r.kend - r.kbeg + kc - 1) / kc);
+}
 
 #define BMQ_IJK(fi, fj)                                          \
     const int i = blockIdx.x * 32 + threadIdx.x;                 \
     const int j = blockIdx.y * BMQ_BY + threadIdx.y;             \
     const int k = kbeg + blockIdx.z * BMQ_BZ + threadIdx.z;      \
     if (i >= (fi) || j >= (fj) || k >= kend_) return;
+
+// Column form of the same index space: a thread owns cells (i, j, kc0..kc1) and walks them in z, so that the planes
+// k-1, k, k+1 its gathers touch are still in L1 when the next cell needs them (a CTA per plane re-fetched them from
+// L2 for every plane).  The map-update and distortion kernels use it; kchunk = 1 is the old one-cell-per-thread form.
+#define BMQ_COLUMN(fi, fj)                                       \
+    const int i = blockIdx.x * 32 + threadIdx.x;                 \
+    const int j = blockIdx.y * BMQ_BY + threadIdx.y;             \
+    const int kc0 = kbeg + blockIdx.z * kchunk;                  \
+    const int kc1 = min(kc0 + kchunk, kend_);
 
 // ------------------------------------------------------------------ forward map (a4)
 // FIX != 0: the x and y extents are the compile-time constant FIX, so that row and plane pitches of
@@ -117,21 +141,24 @@ static inline dim3 grid3(int fi, int fj, KRange r)
 // (each mapper's particle is independent; tracing two per thread doubles the loads in flight).
 template <bool P2, int NMAP, int FIX = 0>
 __global__ void __launch_bounds__(256)
-k_forward(Grid3 g_, int kbeg, int kend_, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
+k_forward(Grid3 g_, int kbeg, int kend_, int kchunk, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
 {
     const Grid3 g = fix_grid<FIX>(g_);
-    BMQ_IJK(g.ni, g.nj)
-    if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
-    const int idx = i + g.ni * (j + g.nj * k);
-    float3 p[NMAP];
+    BMQ_COLUMN(g.ni, g.nj)
+    if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2)) return;
+#pragma unroll 1
+    for (int k = max(kc0, 2); k < min(kc1, g.nk - 2); ++k) {
+        const int idx = i + g.ni * (j + g.nj * k);
+        float3 p[NMAP];
 #pragma unroll
-    for (int m = 0; m < NMAP; ++m) p[m] = make_float3(maps.x[m][idx], maps.y[m][idx], maps.z[m][idx]);
-    trace_multi<P2, NMAP>(vel, g, cfldt, dt, p);
+        for (int m = 0; m < NMAP; ++m) p[m] = make_float3(maps.x[m][idx], maps.y[m][idx], maps.z[m][idx]);
+        trace_multi<P2, NMAP>(vel, g, cfldt, dt, p);
 #pragma unroll
-    for (int m = 0; m < NMAP; ++m) {
-        maps.x[m][idx] = p[m].x;
-        maps.y[m][idx] = p[m].y;
-        maps.z[m][idx] = p[m].z;
+        for (int m = 0; m < NMAP; ++m) {
+            maps.x[m][idx] = p[m].x;
+            maps.y[m][idx] = p[m].y;
+            maps.z[m][idx] = p[m].z;
+        }
     }
 }
 
@@ -149,48 +176,52 @@ __device__ __forceinline__ float dmc_axis(float p, float v, float a, float s)
 
 template <bool P2, int NMAP, int FIX = 0>
 __global__ void __launch_bounds__(256)
-k_dmc(Grid3 g_, int kbeg, int kend_, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
+k_dmc(Grid3 g_, int kbeg, int kend_, int kchunk, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
 {
     const Grid3 g = fix_grid<FIX>(g_);
-    BMQ_IJK(g.ni, g.nj)
-    if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2)) return;
-    const int idx = i + g.ni * (j + g.nj * k);
+    BMQ_COLUMN(g.ni, g.nj)
+    if (!(i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2)) return;
     const float h = g.h;
-    const float px = h * (float)i, py = h * (float)j, pz = h * (float)k;
-    // Two velocity samples.  General h: bit-exact reference arithmetic (lerp_ref in device3d.cuh).
-    // Power-of-two h: both points are grid nodes, where the staggered component has fraction 1/2
-    // and the other two axes fraction 0, so each component is the mean of two faces (2 loads
-    // instead of 8; the dropped terms have weight exactly 0).
-    float3 v0, v1;
-    float tx, ty, tz;
-    if (P2) {
-        v0 = velocity_at_node(vel, g, i, j, k);
-        const int it = v0.x > 0.f ? i - 1 : i + 1, jt = v0.y > 0.f ? j - 1 : j + 1, kt = v0.z > 0.f ? k - 1 : k + 1;
-        tx = v0.x > 0.f ? px - h : px + h;
-        ty = v0.y > 0.f ? py - h : py + h;
-        tz = v0.z > 0.f ? pz - h : pz + h;
-        v1 = velocity_at_node(vel, g, it, jt, kt);
-    } else {
-        v0 = get_velocity_ref(vel, g, px, py, pz);
-        tx = v0.x > 0.f ? px - h : px + h;
-        ty = v0.y > 0.f ? py - h : py + h;
-        tz = v0.z > 0.f ? pz - h : pz + h;
-        v1 = get_velocity_ref(vel, g, tx, ty, tz);
-    }
-    const float ax = (v0.x - v1.x) / (px - tx);
-    const float ay = (v0.y - v1.y) / (py - ty);
-    const float az = (v0.z - v1.z) / (pz - tz);
-    const float nx = dmc_axis(px, v0.x, ax, substep);
-    const float ny = dmc_axis(py, v0.y, ay, substep);
-    const float nz = dmc_axis(pz, v0.z, az, substep);
-    Frac fx = split<P2>(nx, g.h, g.inv_h), fy = split<P2>(ny, g.h, g.inv_h), fz = split<P2>(nz, g.h, g.inv_h);
-    const int sy = g.ni, sz = g.ni * g.nj;
-    const int o = fx.i + sy * fy.i + sz * fz.i;
-#pragma unroll
-    for (int m = 0; m < NMAP; ++m) {
-        out.x[m][idx] = tri8(in.x[m] + o, sy, sz, fx, fy, fz);
-        out.y[m][idx] = tri8(in.y[m] + o, sy, sz, fx, fy, fz);
-        out.z[m][idx] = tri8(in.z[m] + o, sy, sz, fx, fy, fz);
+    const float px = h * (float)i, py = h * (float)j;
+#pragma unroll 1
+    for (int k = max(kc0, 2); k < min(kc1, g.nk - 2); ++k) {
+        const int idx = i + g.ni * (j + g.nj * k);
+        const float pz = h * (float)k;
+        // Two velocity samples.  General h: bit-exact reference arithmetic (lerp_ref in device3d.cuh).
+        // Power-of-two h: both points are grid nodes, where the staggered component has fraction 1/2
+        // and the other two axes fraction 0, so each component is the mean of two faces (2 loads
+        // instead of 8; the dropped terms have weight exactly 0).
+        float3 v0, v1;
+        float tx, ty, tz;
+        if (P2) {
+            v0 = velocity_at_node(vel, g, i, j, k);
+            const int it = v0.x > 0.f ? i - 1 : i + 1, jt = v0.y > 0.f ? j - 1 : j + 1, kt = v0.z > 0.f ? k - 1 : k + 1;
+            tx = v0.x > 0.f ? px - h : px + h;
+            ty = v0.y > 0.f ? py - h : py + h;
+            tz = v0.z > 0.f ? pz - h : pz + h;
+            v1 = velocity_at_node(vel, g, it, jt, kt);
+        } else {
+            v0 = get_velocity_ref(vel, g, px, py, pz);
+            tx = v0.x > 0.f ? px - h : px + h;
+            ty = v0.y > 0.f ? py - h : py + h;
+            tz = v0.z > 0.f ? pz - h : pz + h;
+            v1 = get_velocity_ref(vel, g, tx, ty, tz);
+        }
+        const float ax = (v0.x - v1.x) / (px - tx);
+        const float ay = (v0.y - v1.y) / (py - ty);
+        const float az = (v0.z - v1.z) / (pz - tz);
+        const float nx = dmc_axis(px, v0.x, ax, substep);
+        const float ny = dmc_axis(py, v0.y, ay, substep);
+        const float nz = dmc_axis(pz, v0.z, az, substep);
+        Frac fx = split<P2>(nx, g.h, g.inv_h), fy = split<P2>(ny, g.h, g.inv_h), fz = split<P2>(nz, g.h, g.inv_h);
+        const int sy = g.ni, sz = g.ni * g.nj;
+        const int o = fx.i + sy * fy.i + sz * fz.i;
+    #pragma unroll
+        for (int m = 0; m < NMAP; ++m) {
+            out.x[m][idx] = tri8(in.x[m] + o, sy, sz, fx, fy, fz);
+            out.y[m][idx] = tri8(in.y[m] + o, sy, sz, fx, fy, fz);
+            out.z[m][idx] = tri8(in.z[m] + o, sy, sz, fx, fy, fz);
+        }
     }
 }
 
@@ -531,18 +562,17 @@ k_double_advect(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW
 // atomicMax per block.  Also reduces max |map_z - z| (in world units) per mapper for halo sizing.
 template <bool P2, int NMAP, int FIX = 0>
 __global__ void __launch_bounds__(256)
-k_estimate(Grid3 g_, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
+k_estimate(Grid3 g_, int kbeg, int kend_, int kchunk, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
            const signed char *__restrict__ boundary)
 {
     const Grid3 g = fix_grid<FIX>(g_);
-    const int i = blockIdx.x * 32 + threadIdx.x;
-    const int j = blockIdx.y * BMQ_BY + threadIdx.y;
-    const int k = kbeg + blockIdx.z * BMQ_BZ + threadIdx.z;
-    float d2[NMAP], dispz[NMAP];
+    BMQ_COLUMN(g.ni, g.nj)
+    float d2[NMAP], dispz[NMAP];      // maxima over the column (max is exact and order-free: same bits as one cell per thread)
 #pragma unroll
     for (int m = 0; m < NMAP; ++m) d2[m] = dispz[m] = 0.f;
-    const bool inside = i < g.ni && j < g.nj && k < kend_;
-    if (inside && i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2 && k > 1 && k < g.nk - 2) {
+    const bool column = i > 1 && i < g.ni - 2 && j > 1 && j < g.nj - 2;
+#pragma unroll 1
+    for (int k = max(kc0, 2); column && k < min(kc1, g.nk - 2); ++k) {
         const int idx = i + g.ni * (j + g.nj * k);
         const float px = g.h * (float)i, py = g.h * (float)j, pz = g.h * (float)k;
         const bool counted = boundary == nullptr || boundary[idx] != 2;
@@ -559,8 +589,8 @@ k_estimate(Grid3 g_, int kbeg, int kend_, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd
             const float dfb = (px - b2.x) * (px - b2.x) + (py - b2.y) * (py - b2.y) + (pz - b2.z) * (pz - b2.z);
             const float d = fmaxf(dbf, dfb);
             if (outp.dist[m]) outp.dist[m][idx] = d;
-            if (counted) d2[m] = d;
-            dispz[m] = fmaxf(fabsf(b.z - pz), fabsf(f2.z - pz));
+            if (counted) d2[m] = fmaxf(d2[m], d);
+            dispz[m] = fmaxf(dispz[m], fmaxf(fabsf(b.z - pz), fabsf(f2.z - pz)));
         }
     }
 #pragma unroll
@@ -694,14 +724,15 @@ cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float
 {
     if (r.kend <= r.kbeg) return cudaSuccess;
     Vel3 vel{u, v, w};
-    dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
+    const int kc = column_chunk(g.ni, g.nj, r.kend - r.kbeg);
+    dim3 gr = grid3_columns(g.ni, g.nj, r, kc), bl = block3();
     if (nmap == 1) {
         MapSetRW<1> m; m.x[0] = maps[0][0]; m.y[0] = maps[0][1]; m.z[0] = maps[0][2];
-        DISPATCH_P2_FIX(g, k_forward, 1, g, r.kbeg, r.kend, vel, m, cfldt, dt);
+        DISPATCH_P2_FIX(g, k_forward, 1, g, r.kbeg, r.kend, kc, vel, m, cfldt, dt);
     } else {
         MapSetRW<2> m;
         for (int q = 0; q < 2; ++q) { m.x[q] = maps[q][0]; m.y[q] = maps[q][1]; m.z[q] = maps[q][2]; }
-        DISPATCH_P2_FIX(g, k_forward, 2, g, r.kbeg, r.kend, vel, m, cfldt, dt);
+        DISPATCH_P2_FIX(g, k_forward, 2, g, r.kbeg, r.kend, kc, vel, m, cfldt, dt);
     }
     count_launch();
     return cudaGetLastError();
@@ -713,19 +744,20 @@ cudaError_t launch_dmc(cudaStream_t s, const Grid3 &g, KRange r, const float *u,
 {
     if (r.kend <= r.kbeg) return cudaSuccess;
     Vel3 vel{u, v, w};
-    dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
+    const int kc = column_chunk(g.ni, g.nj, r.kend - r.kbeg);
+    dim3 gr = grid3_columns(g.ni, g.nj, r, kc), bl = block3();
     if (nmap == 1) {
         MapSetRO<1> a; MapSetRW<1> b;
         a.x[0] = in[0][0]; a.y[0] = in[0][1]; a.z[0] = in[0][2];
         b.x[0] = out[0][0]; b.y[0] = out[0][1]; b.z[0] = out[0][2];
-        DISPATCH_P2_FIX(g, k_dmc, 1, g, r.kbeg, r.kend, vel, a, b, substep);
+        DISPATCH_P2_FIX(g, k_dmc, 1, g, r.kbeg, r.kend, kc, vel, a, b, substep);
     } else {
         MapSetRO<2> a; MapSetRW<2> b;
         for (int q = 0; q < 2; ++q) {
             a.x[q] = in[q][0]; a.y[q] = in[q][1]; a.z[q] = in[q][2];
             b.x[q] = out[q][0]; b.y[q] = out[q][1]; b.z[q] = out[q][2];
         }
-        DISPATCH_P2_FIX(g, k_dmc, 2, g, r.kbeg, r.kend, vel, a, b, substep);
+        DISPATCH_P2_FIX(g, k_dmc, 2, g, r.kbeg, r.kend, kc, vel, a, b, substep);
     }
     count_launch();
     return cudaGetLastError();
@@ -953,13 +985,14 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
                             float *const *dispz, const signed char *boundary)
 {
     if (r.kend <= r.kbeg) return cudaSuccess;
-    dim3 gr = grid3(g.ni, g.nj, r), bl = block3();
+    const int kc = column_chunk(g.ni, g.nj, r.kend - r.kbeg);
+    dim3 gr = grid3_columns(g.ni, g.nj, r, kc), bl = block3();
     if (nmap == 1) {
         MapSetRO<1> b, f; DistOut<1> o;
         b.x[0] = bwd[0][0]; b.y[0] = bwd[0][1]; b.z[0] = bwd[0][2];
         f.x[0] = fwd[0][0]; f.y[0] = fwd[0][1]; f.z[0] = fwd[0][2];
         o.dist[0] = dist ? dist[0] : nullptr; o.d2max[0] = d2max ? d2max[0] : nullptr; o.dispz[0] = dispz ? dispz[0] : nullptr;
-        DISPATCH_P2_FIX(g, k_estimate, 1, g, r.kbeg, r.kend, b, f, o, boundary);
+        DISPATCH_P2_FIX(g, k_estimate, 1, g, r.kbeg, r.kend, kc, b, f, o, boundary);
     } else {
         MapSetRO<2> b, f; DistOut<2> o;
         for (int q = 0; q < 2; ++q) {
@@ -968,7 +1001,7 @@ cudaError_t launch_estimate(cudaStream_t s, const Grid3 &g, KRange r, int nmap, 
             o.dist[q] = dist ? dist[q] : nullptr; o.d2max[q] = d2max ? d2max[q] : nullptr;
             o.dispz[q] = dispz ? dispz[q] : nullptr;
         }
-        DISPATCH_P2_FIX(g, k_estimate, 2, g, r.kbeg, r.kend, b, f, o, boundary);
+        DISPATCH_P2_FIX(g, k_estimate, 2, g, r.kbeg, r.kend, kc, b, f, o, boundary);
     }
     count_launch();
     return cudaGetLastError();
