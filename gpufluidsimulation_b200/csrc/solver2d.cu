@@ -223,7 +223,18 @@ struct WorkList {
     int *count;   // device counter
     int *items;   // flat element indices
 };
-__device__ __forceinline__ void defer(const WorkList &wl, int idx) { wl.items[atomicAdd(wl.count, 1)] = idx; }
+// Warp-aggregated append: the lanes of a warp that defer take consecutive slots, so cells that are neighbours in x stay
+// neighbours in the list and the slow pass, one cell per lane, gathers from the same cache lines (with one atomicAdd per
+// lane the list came out shuffled and every load of the slow pass touched up to 32 lines).
+__device__ __forceinline__ void defer(const WorkList &wl, int idx)
+{
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(wl.count, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    wl.items[base + __popc(m & ((1u << lane) - 1u))] = idx;
+}
 
 // updateForward, :1228-1240 (all cells).  SLOW = false: every cell, first solveODE round only,
 // non-converged cells deferred; SLOW = true: the deferred cells, full solveODE.
@@ -1020,6 +1031,18 @@ int bmq2d_accumulate(bmq2d_solver *s, int frame, float dt)
     BMQ_CK(cudaStreamSynchronize(s->stream));
     s->stats.last_remesh = s->lastremeshing; s->stats.last_scalar_remesh = s->rho_lastremeshing;
     s->stats.total_remesh = s->total_resample; s->stats.total_scalar_remesh = s->total_scalar_resample;
+    return BMQ_OK;
+}
+
+// Sizes of the six work lists of the last step (cells whose solveODE needed more than the first round): forward
+// maps (velocity, scalar), semi-Lagrangian rho, T, u, v.  Synchronises; a diagnostic, not part of the step.
+int bmq2d_deferred_counts(bmq2d_solver *s, int *counts6)
+{
+    NEED2(s);
+    if (!counts6) return bmq::set_error(BMQ_ERR_ARG, "bmq2d_deferred_counts: counts6 is null");
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    for (int w = 0; w < 6; ++w)
+        BMQ_CK(cudaMemcpy(&counts6[w], s->d_wl + w * s->wl_stride, sizeof(int), cudaMemcpyDeviceToHost));
     return BMQ_OK;
 }
 

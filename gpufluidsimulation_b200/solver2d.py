@@ -91,5 +91,11 @@ class BimocqAdvection2D:
         check(self.lib.bmq2d_get_stats(self._h, C.byref(st)), "bmq2d_get_stats")
         return st.as_dict()
 
+    def deferred_counts(self):
+        """Cells of the last step whose solveODE went past its first round, per work list (diagnostic; synchronises)."""
+        c = (C.c_int * 6)()
+        check(self.lib.bmq2d_deferred_counts(self._h, c), "bmq2d_deferred_counts")
+        return list(c)
+
     def launches(self):
         return int(self.lib.bmq2d_kernel_launch_count(self._h))

@@ -455,6 +455,9 @@ int bmq2d_advect(bmq2d_solver *s, int frame, float dt);
 /* lines 449-507: on entry U_FORCED/V_FORCED = velocity after forces, U,V,RHO,T = after projection */
 int bmq2d_accumulate(bmq2d_solver *s, int frame, float dt);
 int bmq2d_get_stats(bmq2d_solver *s, bmq2d_stats *out);
+/* diagnostic: cells of the last step whose solveODE went past its first round, per work list (forward maps velocity /
+ * scalar, semi-Lagrangian rho, T, u, v); synchronises */
+int bmq2d_deferred_counts(bmq2d_solver *s, int *counts6);
 int bmq2d_advect_host(bmq2d_solver *s, int frame, float dt, float *u, float *v, float *rho, float *T);
 int bmq2d_accumulate_host(bmq2d_solver *s, int frame, float dt, const float *u_forced, const float *v_forced,
                           float *u_final, float *v_final, const float *rho_final, const float *T_final);

@@ -34,9 +34,13 @@ __global__ void __launch_bounds__(256) k(const float *a, const float *b, const f
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
-int main()
+int main(int argc, char **argv)
 {
-    const int span = 1 << 16;                      // 256 KB per array as float; float4 view = 1 MB: L2 resident
+    // default 1 << 16: 256 KB per array as float (float4 view = 1 MB): L2 resident, L1 misses.
+    // 1 << 12 (16 KB per array, 64 KB as float4): everything hits L1 -- the regime of the gather kernels (L1 hit
+    // rate 88-94 %), where a staged shared-memory tile would have to beat the LDG
+    const int span = argc > 1 ? 1 << atoi(argv[1]) : 1 << 16;
+    printf("span = %d floats per array\n", span);
     float *buf, *out;
     cudaMalloc(&buf, sizeof(float) * span * 4 * 4);
     cudaMemset(buf, 0, sizeof(float) * span * 4 * 4);
