@@ -59,6 +59,36 @@ __device__ __forceinline__ void prefetch_line(const float *p)
 #endif
 }
 
+// Timing experiments only: the marginal cost, inside the real kernels, of one more load per gathered node.  The
+// extra load's bits are AND-ed with a run-time zero and OR-ed into the value, so results stay exact and the
+// compiler cannot drop it.  3: the same (misaligned) global load again; 4: a shared-memory load; 5: a global load
+// aligned to its 128-byte line.  profiles/r2_march_variants.md
+#ifndef BMQ_HACK_GATHER
+#define BMQ_HACK_GATHER 0
+#endif
+#if BMQ_HACK_GATHER == 4
+extern __shared__ float bmq_hack_smem[];
+#endif
+__device__ __forceinline__ float gld(const float *p, unsigned zero)
+{
+    const float v = __ldg(p);
+#if BMQ_HACK_GATHER == 3
+    float e;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(e) : "l"(p));
+#elif BMQ_HACK_GATHER == 4
+    const float e = bmq_hack_smem[(reinterpret_cast<size_t>(p) >> 2) & 1023];
+#elif BMQ_HACK_GATHER == 5
+    float e;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(e) : "l"(reinterpret_cast<const float *>(reinterpret_cast<size_t>(p) & ~size_t(127)) + (threadIdx.x & 31)));
+#endif
+#if BMQ_HACK_GATHER >= 3
+    return __int_as_float(__float_as_int(v) | (__float_as_int(e) & (int)zero));
+#else
+    (void)zero;
+    return v;
+#endif
+}
+
 template <int NF, int NS> struct MarchArgs {
     float *out[NF];          // advect: f_adv | error: e0 | cumulate: target (read-modify-write) | apply: f
     const float *src[NS];    // gathered through the map: init | f_adv | change sets [set][field] | e0
@@ -184,17 +214,17 @@ __device__ __forceinline__ Split2 split2(float2 q)
 // two trilinear samples (the two lanes) of NS co-located fields; lane arithmetic = tri8 (device3d.cuh)
 template <int NS>
 __device__ __forceinline__ void gather_pair(const float *const (&src)[NS], int sy, int sz, const Split2 &x, const Split2 &y,
-                                            const Split2 &z, float (&lane0)[NS], float (&lane1)[NS])
+                                            const Split2 &z, float (&lane0)[NS], float (&lane1)[NS], unsigned zero = 0)
 {
     const int o0 = x.i0 + sy * y.i0 + sz * z.i0, o1 = x.i1 + sy * y.i1 + sz * z.i1;
 #pragma unroll
     for (int f = 0; f < NS; ++f) {
         const float *p0 = src[f] + o0, *p1 = src[f] + o1;
-        const float2 n000 = make_float2(__ldg(p0), __ldg(p1)), n001 = make_float2(__ldg(p0 + 1), __ldg(p1 + 1));
-        const float2 n010 = make_float2(__ldg(p0 + sy), __ldg(p1 + sy)), n011 = make_float2(__ldg(p0 + sy + 1), __ldg(p1 + sy + 1));
-        const float2 n100 = make_float2(__ldg(p0 + sz), __ldg(p1 + sz)), n101 = make_float2(__ldg(p0 + sz + 1), __ldg(p1 + sz + 1));
-        const float2 n110 = make_float2(__ldg(p0 + sz + sy), __ldg(p1 + sz + sy));
-        const float2 n111 = make_float2(__ldg(p0 + sz + sy + 1), __ldg(p1 + sz + sy + 1));
+        const float2 n000 = make_float2(gld(p0, zero), gld(p1, zero)), n001 = make_float2(gld(p0 + 1, zero), gld(p1 + 1, zero));
+        const float2 n010 = make_float2(gld(p0 + sy, zero), gld(p1 + sy, zero)), n011 = make_float2(gld(p0 + sy + 1, zero), gld(p1 + sy + 1, zero));
+        const float2 n100 = make_float2(gld(p0 + sz, zero), gld(p1 + sz, zero)), n101 = make_float2(gld(p0 + sz + 1, zero), gld(p1 + sz + 1, zero));
+        const float2 n110 = make_float2(gld(p0 + sz + sy, zero), gld(p1 + sz + sy, zero));
+        const float2 n111 = make_float2(gld(p0 + sz + sy + 1, zero), gld(p1 + sz + sy + 1, zero));
         const float2 a00 = lerp32x2(n000, n001, x.f, x.omf), a01 = lerp32x2(n010, n011, x.f, x.omf);
         const float2 a10 = lerp32x2(n100, n101, x.f, x.omf), a11 = lerp32x2(n110, n111, x.f, x.omf);
         const float2 b0 = lerp32x2(a00, a01, y.f, y.omf), b1 = lerp32x2(a10, a11, y.f, y.omf);
@@ -247,6 +277,7 @@ __global__ void __launch_bounds__(32 * BMQ_MARCH_BY, BMQ_MARCH_MINBLOCKS)
 k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map3 m)
 {
     const Grid3 g = fix_grid<FIX>(g_);
+    const unsigned hack_zero = BMQ_HACK_GATHER ? (unsigned)g_.nk >> 30 : 0u;     // 0 at run time, unknown at compile time
     constexpr int DX = STAG == 1, DY = STAG == 2, DZ = STAG == 3, NZ = STAG == 3 ? 2 : 3, NS = NF * NCH;
     constexpr int GL = MODE == GM_ADVECT ? 2 : 1;     // interior guard GL + D < idx < f - GL - 1 (reference :341/:405/:467)
     const int fi = g.ni + DX, fj = g.nj + DY, fk = g.nk + DZ;
@@ -368,7 +399,7 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
                 qz.y = to_cells<P2>(clampf(pz[ii].y, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
                 const Split2 spx = split2(qx), spy = split2(qy), spz = split2(qz);
                 float s0[NS];
-                gather_pair<NS>(a.src, fi, fplane, spx, spy, spz, s0, late[ii]);
+                gather_pair<NS>(a.src, fi, fplane, spx, spy, spz, s0, late[ii], hack_zero);
 #pragma unroll
                 for (int f = 0; f < NS; ++f) sum[f] = fmaf(wgt[f], s0[f], sum[f]);
             }
@@ -472,7 +503,7 @@ static inline int march_chunk(int fi, int fj, int nplanes)
 }
 
 #define BMQ_MARCH_CASE(MODE, P2V, STAGV, NFV, NCHV, FIXV)                                                     \
-    k_march<MODE, P2V, STAGV, NFV, NCHV, FIXV><<<gr, bl, 0, s>>>(g, r.kbeg, r.kend, kc, a, m)
+    k_march<MODE, P2V, STAGV, NFV, NCHV, FIXV><<<gr, bl, BMQ_HACK_GATHER == 4 ? 4096 : 0, s>>>(g, r.kbeg, r.kend, kc, a, m)
 #define BMQ_MARCH_FIX(MODE, P2V, STAGV, NFV, NCHV)                                                            \
     switch (fix) {                                                                                            \
     case 512: BMQ_MARCH_CASE(MODE, P2V, STAGV, NFV, NCHV, 512); break;                                        \
