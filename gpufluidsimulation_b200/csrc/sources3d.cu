@@ -144,8 +144,36 @@ k_mad(float *field, const float *f1, const float *f2, float c1, float c2, size_t
 //     scenes (L = 0.2) every thread addresses cell (0,0,0) or (-1,..);
 //   * the scatter: several threads may write the same fieldTemp cell (a race in the reference; the
 //     result there is the value of whichever thread wins -- same here).
-// Only difference: reads past the end of `field` return 0 and writes outside fieldTemp are dropped
+// Only difference: reads outside `field` / u / v / w return 0 and writes outside fieldTemp are dropped
 // (the reference accesses whatever memory is there).
+// get_velocity_ref / tri8_ref (device3d.cuh) with every node read guarded: the reference samples the velocity half a
+// cell past the last face of a staggered field (point = h * (index + 0.5), :900) and wherever a wild back-trace lands;
+// nodes outside the arrays read as 0 here instead of whatever memory is there.  In-range arithmetic is unchanged.
+__device__ __forceinline__ float tri8_ref_guarded(const float *__restrict__ base, long long n, long long sy, long long sz,
+                                                  const bmq::Frac &x, const bmq::Frac &y, const bmq::Frac &z)
+{
+    const long long o = (long long)x.i + sy * y.i + sz * z.i;
+    auto at = [&](long long q) -> float { return q >= 0 && q < n ? __ldg(base + q) : 0.f; };
+    const float v000 = at(o), v001 = at(o + 1), v010 = at(o + sy), v011 = at(o + sy + 1);
+    const float v100 = at(o + sz), v101 = at(o + sz + 1), v110 = at(o + sz + sy), v111 = at(o + sz + sy + 1);
+    const float a0 = bmq::lerp_ref(v000, v001, x.f), a1 = bmq::lerp_ref(v010, v011, x.f);
+    const float a2 = bmq::lerp_ref(v100, v101, x.f), a3 = bmq::lerp_ref(v110, v111, x.f);
+    return bmq::lerp_ref(bmq::lerp_ref(a0, a1, y.f), bmq::lerp_ref(a2, a3, y.f), z.f);
+}
+__device__ __forceinline__ float3 get_velocity_ref_guarded(const bmq::Vel3 &vel, const bmq::Grid3 &g, float px, float py, float pz)
+{
+    const float hh = 0.5f * g.h;
+    const bmq::Frac x0 = bmq::split<false>(px, g.h, g.inv_h), x5 = bmq::split<false>(px + hh, g.h, g.inv_h);
+    const bmq::Frac y0 = bmq::split<false>(py, g.h, g.inv_h), y5 = bmq::split<false>(py + hh, g.h, g.inv_h);
+    const bmq::Frac z0 = bmq::split<false>(pz, g.h, g.inv_h), z5 = bmq::split<false>(pz + hh, g.h, g.inv_h);
+    const long long ni = g.ni, nj = g.nj, nk = g.nk;
+    float3 r;
+    r.x = tri8_ref_guarded(vel.u, (ni + 1) * nj * nk, ni + 1, (ni + 1) * nj, x5, y0, z0);
+    r.y = tri8_ref_guarded(vel.v, ni * (nj + 1) * nk, ni, ni * (nj + 1), x0, y5, z0);
+    r.z = tri8_ref_guarded(vel.w, ni * nj * (nk + 1), ni, ni * nj, x0, y0, z5);
+    return r;
+}
+
 __global__ void __launch_bounds__(128)
 k_clamp_extrema_mc(const float *__restrict__ field, float *fieldTemp, bmq::Vel3 vel, int ni, int nj, int nk, int dimx,
                    int dimy, int dimz, float ox, float oy, float oz, float h, float dt)
@@ -155,10 +183,10 @@ k_clamp_extrema_mc(const float *__restrict__ field, float *fieldTemp, bmq::Vel3 
     bmq::Grid3 g;
     g.ni = ni - dimx; g.nj = nj - dimy; g.nk = nk - dimz; g.h = h; g.inv_h = -(1.0f / h);   // negative: IEEE division (device3d.cuh)
     const float ptx = h * (float(i) + ox), pty = h * (float(j) + oy), ptz = h * (float(k) + oz);
-    float3 v = bmq::get_velocity_ref(vel, g, ptx, pty, ptz);
+    float3 v = get_velocity_ref_guarded(vel, g, ptx, pty, ptz);
     const float halfdt = 0.5f * dt;
     float pxx = ptx - v.x * halfdt, pxy = pty - v.y * halfdt, pxz = ptz - v.z * halfdt;
-    v = bmq::get_velocity_ref(vel, g, pxx, pxy, pxz);
+    v = get_velocity_ref_guarded(vel, g, pxx, pxy, pxz);
     pxx = ptx - v.x * dt; pxy = pty - v.y * dt; pxz = ptz - v.z * dt;
     const int gi = (int)floor(pxx), gj = (int)floor(pxy), gk = (int)floor(pxz);
     const float cx = pxx - (float)gi, cy = pxy - (float)gj, cz = pxz - (float)gk;

@@ -1,6 +1,7 @@
 """Host-side mirror of the reference's device-resident smoke solver, ``BimocqGPUSolver``
-(bimocq3D/BimocqGPUSolver.{h,cpp}), BIMOCQ scheme: same members, same call sequence
-(``advanceBimocq``, BimocqGPUSolver.cpp:128-232), every device operation going through the legacy
+(bimocq3D/BimocqGPUSolver.{h,cpp}), both of its schemes: same members, same call sequences
+(``advanceBimocq``, BimocqGPUSolver.cpp:128-232; ``advanceReflection``, the MacCormack + reflection scheme,
+:232-335; ``semilagAdvect``, :337-344), every device operation going through the legacy
 ``gpu_*`` symbols exactly as ``gpuMapper`` forwards them (GPU_Advection.h:328-626).
 
 It exists to show -- and test -- that libbimocq_b200.so replaces the WHOLE frame of that solver
@@ -136,8 +137,100 @@ class BimocqGPUSolver:
             getattr(self, n + "Prev").copy_(getattr(self, n + "Init"))
             getattr(self, n + "Init").copy_(getattr(self, n))
 
-    def advance(self, framenum, dt):
-        self.advanceBimocq(framenum, dt)
+    # BimocqGPUSolver.cpp:109-126
+    def advance(self, framenum, dt, scheme="BIMOCQ"):
+        if scheme == "BIMOCQ":
+            self.advanceBimocq(framenum, dt)
+        elif scheme == "MAC_REFLECTION":
+            self.advanceReflection(framenum, dt)
+        else:
+            raise ValueError(f"unknown scheme {scheme!r} (the reference's GPU solver has BIMOCQ and MAC_REFLECTION)")
+
+    # ---- gpuMapper's forwarding members used by the non-BiMocq schemes (GPU_Advection.h:530-551, 610-613)
+    def _semilagAdvectField(self, field, field_src, cfldt, dt):
+        nx, ny, nz = self.CellNumberX, self.CellNumberY, self.CellNumberZ
+        field.zero_()      # the reference clears (ni+1)*nj*nk floats of a centred buffer; the in-range part is what matters
+        self.lib.gpu_semilag(_dp(field), _dp(field_src), _dp(self.VelocityU), _dp(self.VelocityV), _dp(self.VelocityW),
+                             0, 0, 0, self.CellSize, nx, ny, nz, cfldt, dt)
+
+    def _semilagAdvectVelocity(self, outs, srcs, cfldt, dt):
+        nx, ny, nz = self.CellNumberX, self.CellNumberY, self.CellNumberZ
+        vel = (_dp(self.VelocityU), _dp(self.VelocityV), _dp(self.VelocityW))
+        for o in outs:
+            o.zero_()
+        for o, src, dims in zip(outs, srcs, ((1, 0, 0), (0, 1, 0), (0, 0, 1))):
+            self.lib.gpu_semilag(_dp(o), _dp(src), *vel, *dims, self.CellSize, nx, ny, nz, cfldt, dt)
+
+    def _clampExtrema(self, field, fieldTemp, dims, origin, dt):
+        nx, ny, nz = self.CellNumberX, self.CellNumberY, self.CellNumberZ
+        self.lib.gpu_clamp_extrema(_dp(field), _dp(fieldTemp), _dp(self.VelocityU), _dp(self.VelocityV), _dp(self.VelocityW),
+                                   nx + dims[0], ny + dims[1], nz + dims[2], *dims, *origin, self.CellSize, dt)
+
+    def _mad(self, field, f1, f2, c1, c2):
+        self.lib.gpu_mad(_dp(field), _dp(f1), _dp(f2), c1, c2, field.numel())
+
+    def _maccormack_velocity(self, srcs, cfldt, half_dt):
+        """srcs advected back over half_dt with the MacCormack correction and the extrema clamp, result copied into
+        the velocity (the block that appears twice in advanceReflection, BimocqGPUSolver.cpp:264-283 and :312-333)."""
+        vel = (self.VelocityU, self.VelocityV, self.VelocityW)
+        tmp = (self.VelocityUTemp, self.VelocityVTemp, self.VelocityWTemp)
+        back = (self.TempSrcU, self.TempSrcV, self.TempSrcW)
+        self._semilagAdvectVelocity(tmp, srcs, cfldt, -half_dt)
+        self._semilagAdvectVelocity(back, tmp, cfldt, half_dt)
+        for t, b in zip(tmp, back):
+            self._add(t, b, -0.5)
+        for t, s_ in zip(tmp, srcs):
+            self._add(t, s_, 0.5)
+        for v_, t, dims, org in zip(vel, tmp, ((1, 0, 0), (0, 1, 0), (0, 0, 1)), ((0.5, 0.0, 0.0), (0.0, 0.5, 0.0), (0.0, 0.0, 0.5))):
+            self._clampExtrema(v_, t, dims, org, half_dt)
+        for v_, t in zip(vel, tmp):
+            v_.copy_(t)
+        self._check("MacCormack velocity advection")
+
+    # BimocqGPUSolver.cpp:232-335
+    def advanceReflection(self, framenum, dt):
+        nx, ny, nz = self.CellNumberX, self.CellNumberY, self.CellNumberZ
+        cfldt = self.getCFL()
+        vel = (self.VelocityU, self.VelocityV, self.VelocityW)
+        tmp = (self.VelocityUTemp, self.VelocityVTemp, self.VelocityWTemp)
+        proj = (self.duProj, self.dvProj, self.dwProj)
+        for field, ftemp in ((self.Density, self.DensityTemp), (self.Temperature, self.TemperatureTemp)):
+            self._semilagAdvectField(ftemp, field, cfldt, -dt)
+            self._semilagAdvectField(self.TempSrcU, ftemp, cfldt, dt)     # the reference borrows TempSrcU (u-sized) here
+            self._add_n(ftemp, self.TempSrcU, -0.5, nx * ny * nz)
+            self._add_n(ftemp, field, 0.5, nx * ny * nz)
+            self._clampExtrema(field, ftemp, (0, 0, 0), (0.0, 0.0, 0.0), dt)
+            field.copy_(ftemp)
+        self._maccormack_velocity(vel, cfldt, 0.5 * dt)
+        self.emitSmoke(framenum, dt)
+        self.addBuoyancy(0.5 * dt)
+        if self.Viscosity:
+            self.diffuseField(vel[0], tmp[0], self.TempSrcU, nx + 1, ny, nz, 20, self.Viscosity, 0.5 * dt)
+            self.diffuseField(vel[1], tmp[1], self.TempSrcV, nx, ny + 1, nz, 20, self.Viscosity, 0.5 * dt)
+            self.diffuseField(vel[2], tmp[2], self.TempSrcW, nx, ny, nz + 1, 20, self.Viscosity, 0.5 * dt)
+        for t, v_ in zip(tmp, vel):
+            t.copy_(v_)
+        self.projection()
+        for p_, v_, t in zip(proj, vel, tmp):
+            self._mad(p_, v_, t, 2.0, -1.0)                 # the reflected velocity 2 u_projected - u_before
+        self._maccormack_velocity(proj, cfldt, 0.5 * dt)
+        self.addBuoyancy(0.5 * dt)
+        if self.Viscosity:
+            self.diffuseField(vel[0], tmp[0], self.TempSrcU, nx + 1, ny, nz, 20, self.Viscosity, 0.5 * dt)
+            self.diffuseField(vel[1], tmp[1], self.TempSrcV, nx, ny + 1, nz, 20, self.Viscosity, 0.5 * dt)
+            self.diffuseField(vel[2], tmp[2], self.TempSrcW, nx, ny, nz + 1, 20, self.Viscosity, 0.5 * dt)
+        self.projection()
+
+    # BimocqGPUSolver.cpp:337-344
+    def semilagAdvect(self, cfldt, dt):
+        self._semilagAdvectVelocity((self.VelocityUTemp, self.VelocityVTemp, self.VelocityWTemp),
+                                    (self.VelocityU, self.VelocityV, self.VelocityW), cfldt, dt)
+        self._semilagAdvectField(self.DensityTemp, self.Density, cfldt, dt)
+        self._semilagAdvectField(self.TemperatureTemp, self.Temperature, cfldt, dt)
+        self._check("gpu_semilag")
+
+    def _add_n(self, f1, f2, coeff, number):
+        self.lib.gpu_add(_dp(f1), _dp(f2), coeff, number)
 
     # BimocqGPUSolver.cpp:128-232
     def advanceBimocq(self, framenum, dt):
@@ -199,7 +292,8 @@ class BimocqGPUSolver:
 
     FIELDS = ("VelocityU", "VelocityV", "VelocityW", "Density", "Temperature", "VelocityUInit", "VelocityVInit",
               "VelocityWInit", "VelocityUPrev", "VelocityVPrev", "VelocityWPrev", "DensityInit", "TemperatureInit",
-              "DensityPrev", "TemperaturePrev", "duExtern", "dvExtern", "dwExtern", "duProj", "dvProj", "dwProj", "p")
+              "DensityPrev", "TemperaturePrev", "duExtern", "dvExtern", "dwExtern", "duProj", "dvProj", "dwProj", "p",
+              "VelocityUTemp", "VelocityVTemp", "VelocityWTemp", "DensityTemp", "TemperatureTemp")
 
     def snapshot(self):
         """Host copies of every state field (tests)."""
