@@ -182,6 +182,9 @@ __device__ __forceinline__ void floor_index(float q, float &fl, int &i)
 #if BMQ_SPLIT_MODE == 1
     i = __float2int_rd(q);
     fl = __fadd_rn(__int_as_float(0x4B000000 | i), -8388608.0f);
+#elif BMQ_SPLIT_MODE == 3
+    i = __float2int_rd(q);              // F2I.FLOOR + I2FP: the integer-to-float conversion is exact here (|i| < 2^22)
+    fl = (float)i;
 #elif BMQ_SPLIT_MODE == 2
     const float t = __fadd_rn(q, 8388608.0f);            // integer-valued float in [2^23, 2^24): RN(q) + 2^23
     const float r = __fadd_rn(t, -8388608.0f);           // RN(q), exact
