@@ -1022,6 +1022,7 @@ struct bmq3d_mg {
     bmq3d_solver *s = nullptr;
     int rank = 0, world = 1;
     cudaStream_t copy = nullptr, copy2 = nullptr;   // copy: barrier + pulls from the lower side; copy2: pulls from the upper side
+    cudaStream_t red = nullptr;                     // the distortion reduction, beside the scalar accumulation
     cudaEvent_t ev[MG_EVENTS] = {};                 // transient events (waited for right after they are recorded)
     int ev_next = 0;
     cudaEvent_t done_ev[MG_DONE_EVENTS] = {};       // completion of the posted exchanges, one per purpose (see MgDone)
@@ -1145,6 +1146,26 @@ int mg_exchange(bmq3d_mg *m, const MgGroup *groups, int ngroups)
     return mg_wait(m, MG_D_BLOCKING);
 }
 
+// Device-flag signalling only: the reduction as two halves, so that work that does not depend on the result can be
+// queued in between.  begin: the one-warp mailbox kernel on the side stream `red`, after everything queued on the
+// compute stream so far (dev_vals = result of a kernel there).  end: wait for it, hand out the maxima.
+int mg_reduce_begin(bmq3d_mg *m, int n, const float *dev_vals)
+{
+    if (n > MG_RED_MAX) return set_error(BMQ_ERR_ARG, "bmq3d_mg: reduction of %d values", n);
+    cudaEvent_t produced = mg_event(m);
+    BMQ_CK(cudaEventRecord(produced, m->s->stream));
+    BMQ_CK(cudaStreamWaitEvent(m->red, produced, 0));
+    BMQ_CK(launch_mg_allreduce_max(m->red, m->sig, m->other_ranks, nullptr, dev_vals, n, ++m->red_seq, m->red_host));
+    return BMQ_OK;
+}
+int mg_reduce_end(bmq3d_mg *m, float *vals, int n)
+{
+    BMQ_CK(cudaStreamSynchronize(m->red));
+    if (m->red_host[MG_RED_MAX] != 0.f) return set_error(BMQ_ERR_CUDA, "bmq3d_mg: a peer did not answer within 30 s (rank %d)", m->rank);
+    for (int q = 0; q < n; ++q) vals[q] = m->red_host[q];
+    return BMQ_OK;
+}
+
 // dev_vals != nullptr (device-flag signalling only): this rank's contribution is still on the device, `vals` receives the maxima
 int mg_reduce(bmq3d_mg *m, float *vals, int n, const float *dev_vals = nullptr)
 {
@@ -1213,6 +1234,7 @@ int bmq3d_mg_create(int ni, int nj, int nk, float h, float blend_coeff, int rank
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         st = check_cuda(cudaStreamCreateWithPriority(&m->copy, cudaStreamNonBlocking, hi), "cudaStreamCreate", __FILE__, __LINE__);
         if (st == BMQ_OK) st = check_cuda(cudaStreamCreateWithPriority(&m->copy2, cudaStreamNonBlocking, hi), "cudaStreamCreate", __FILE__, __LINE__);
+        if (st == BMQ_OK) st = check_cuda(cudaStreamCreateWithPriority(&m->red, cudaStreamNonBlocking, hi), "cudaStreamCreate", __FILE__, __LINE__);
     }
     if (st == BMQ_OK && world > MG_MAX_WORLD) st = set_error(BMQ_ERR_ARG, "bmq3d_mg_create: at most %d ranks", (int)MG_MAX_WORLD);
     // its own 2 MB allocation: a CUDA IPC handle names a whole allocation, and a block shared with other small
@@ -1240,6 +1262,7 @@ int bmq3d_mg_destroy(bmq3d_mg *m)
     for (auto e : m->done_ev) if (e) cudaEventDestroy(e);
     if (m->copy) cudaStreamDestroy(m->copy);
     if (m->copy2) cudaStreamDestroy(m->copy2);
+    if (m->red) cudaStreamDestroy(m->red);
     if (m->sig) cudaFree(m->sig);
     if (m->red_host) cudaFreeHost(m->red_host);
     if (m->s) bmq3d_destroy(m->s);
@@ -1501,9 +1524,16 @@ int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt)
         RET_IF(mg_post(m, gv, 1, MG_D_CH_V));
     }
     float red[4] = {0, 0, 0, 0};
-    if (m->world > 1 && m->signal_mode != BMQ_MG_SIGNAL_HOST) {
+    const bool on_device = m->world > 1 && m->signal_mode != BMQ_MG_SIGNAL_HOST;
+    if (on_device) {
+        // The scalars' accumulation does not depend on the re-initialisation decision (the velocity's does, through the
+        // projection coefficient): it is queued BEFORE the host waits for the reduced distortion, and the reduction runs
+        // beside it on its own stream.  The wait for the slowest rank and the host round trip hide behind it.
         RET_IF(stage_distortion(s, nullptr, nullptr, nullptr));
-        RET_IF(mg_reduce(m, red, 4, s->d_red + 1));
+        RET_IF(mg_reduce_begin(m, 4, s->d_red + 1));
+        RET_IF(mg_wait(m, MG_D_CH_S));
+        RET_IF(stage_accumulate(s, 1));
+        RET_IF(mg_reduce_end(m, red, 4));
         red[2] /= s->h; red[3] /= s->h;                         // as stage_distortion reports them: in cells
     } else {
         RET_IF(stage_distortion(s, &red[0], &red[1], &red[2]));     // red[2], red[3] = z displacement per mapper
@@ -1513,8 +1543,10 @@ int bmq3d_mg_accumulate(bmq3d_mg *m, int framenum, float dt)
     s->stats.max_disp_z_vel = red[2]; s->stats.max_disp_z_scalar = red[3];
     s->stats.max_disp_z = red[2] > red[3] ? red[2] : red[3];
     decide(s, framenum, dt, red[0], red[1]);
-    if (m->world > 1) RET_IF(mg_wait(m, MG_D_CH_S));
-    RET_IF(stage_accumulate(s, 1));         // independent of the velocity's accumulation: any order gives the same fields
+    if (!on_device) {
+        if (m->world > 1) RET_IF(mg_wait(m, MG_D_CH_S));
+        RET_IF(stage_accumulate(s, 1));         // independent of the velocity's accumulation: any order gives the same fields
+    }
     if (m->world > 1) RET_IF(mg_wait(m, MG_D_CH_V));
     RET_IF(stage_accumulate(s, 0));
     if (s->vel_reinit) {
