@@ -72,3 +72,22 @@ def test_no_cpu_fallback_without_device(lib):
     assert st != 0 and not h.value
     assert b"no CUDA device" in lib.bmq_last_error() or b"CUDA" in lib.bmq_last_error()
     lib.bmq_clear_error()
+
+
+def test_argument_errors_of_the_round_two_entry_points(lib):
+    """Null handles and bad modes are reported through the status code and the error latch (no GPU needed)."""
+    for call in (lambda: lib.bmq3d_mg_set_signalling(None, 1),
+                 lambda: lib.bmq3d_timing_read_gaps(None, None, None, None, 16),
+                 lambda: lib.bmq2d_deferred_counts(None, None),
+                 lambda: lib.bmq3d_mg_advect(None, 0, 0.01),
+                 lambda: lib.bmq3d_mg_accumulate(None, 0, 0.01)):
+        lib.bmq_clear_error()
+        assert call() != 0
+        assert lib.bmq_last_error() != b""
+    lib.bmq_clear_error()
+
+
+def test_signalling_modes_match_header():
+    text = open(capi.header_path()).read()
+    m = re.search(r"BMQ_MG_SIGNAL_AUTO = (-?\d+), BMQ_MG_SIGNAL_HOST = (\d+), BMQ_MG_SIGNAL_DEVICE = (\d+), BMQ_MG_SIGNAL_DEVICE_CE = (\d+)", text)
+    assert m and [int(x) for x in m.groups()] == [-1, 0, 1, 2]
