@@ -556,6 +556,7 @@ def measure_2d(torch, n=1024, steps=20, warm=5, cpu_leg=True):
     nsub = s.stats()["n_substeps"]
     out = {"workload": f"BiMocq2D vortex-in-a-box {n}x{n}, velocity + 2 scalars", "ms_per_step": ms,
            "solveode_deferred_cells_last_step": s.deferred_counts(),
+           "solveode_cells_entering_round_1_to_6": s.deferred_round_counts(),
            "cell_updates_per_s": n * n / (ms * 1e-3), "n_sub": nsub, "kernel_launches_per_step": (s.launches() - l0) / steps,
            "alg_bytes_per_cell_update": 424 + 40 * nsub,
            "hbm_roofline_frac": (424 + 40 * nsub) * n * n / (ms * 1e-3) / 1e9 / measured_peak()[0],

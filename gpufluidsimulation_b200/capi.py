@@ -188,6 +188,7 @@ _PROTOS = {
     "bmq2d_accumulate": (_I, [_H, _I, _f]),
     "bmq2d_get_stats": (_I, [_H, C.POINTER(Stats2D)]),
     "bmq2d_deferred_counts": (_I, [_H, C.POINTER(_I)]),
+    "bmq2d_deferred_round_counts": (_I, [_H, C.POINTER(_I)]),
     "bmq2d_advect_host": (_I, [_H, _I, _f] + [C.c_void_p] * 4),
     "bmq2d_accumulate_host": (_I, [_H, _I, _f] + [C.c_void_p] * 6),
     "bmq2d_kernel_launch_count": (C.c_ulonglong, [_H]),

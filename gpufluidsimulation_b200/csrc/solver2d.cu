@@ -218,46 +218,71 @@ __device__ __forceinline__ V2 map_through(const G2 &g, const float *mx, const fl
     const int idx = i + (fni) * j;
 
 // ---------------------------------------------------------------- kernels
-// Work list of the cells whose solveODE did not converge in the first round.
+// Work list of the cells whose solveODE has not converged yet: the cell and the result of its last round (the
+// reference's pos1 of the next comparison).
 struct WorkList {
     int *count;   // device counter
     int *items;   // flat element indices
+    float *px, *py;
 };
-// Warp-aggregated append: the lanes of a warp that defer take consecutive slots, so cells that are neighbours in x stay
-// neighbours in the list and the slow pass, one cell per lane, gathers from the same cache lines (with one atomicAdd per
-// lane the list came out shuffled and every load of the slow pass touched up to 32 lines).
-__device__ __forceinline__ void defer(const WorkList &wl, int idx)
+// Warp-aggregated append: the lanes of a warp that defer take consecutive slots (one atomicAdd per warp).
+__device__ __forceinline__ void defer(const WorkList &wl, int idx, V2 last)
 {
     const unsigned m = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
     int base = 0;
     if (lane == leader) base = atomicAdd(wl.count, __popc(m));
     base = __shfl_sync(m, base, leader);
-    wl.items[base + __popc(m & ((1u << lane) - 1u))] = idx;
+    const int e = base + __popc(m & ((1u << lane) - 1u));
+    wl.items[e] = idx;
+    wl.px[e] = last.x;
+    wl.py[e] = last.y;
 }
 
-// updateForward, :1228-1240 (all cells).  SLOW = false: every cell, first solveODE round only,
-// non-converged cells deferred; SLOW = true: the deferred cells, full solveODE.
-template <bool SLOW>
+// Round r = 1..6 of solveODE (:30-41) for ONE cell whose previous round gave `last`: 2^(r+1) RK3 steps of dt / 2^(r+1)
+// from the start position; returns true when the reference's loop stops after this round (the two last rounds agree
+// to 1e-4 h, or six halvings are done).  Rounds are launched one after the other over compacted lists, so a warp
+// never waits for one lane's 254 steps while its other lanes are done after 4 (the single slow pass of round 1 did).
+__device__ __forceinline__ bool solve_ode_round(const G2 &g, const float *u, const float *v, float dt, int r, V2 pos, V2 last, V2 &out)
+{
+    float ddt = dt;
+    int substeps = 1;
+    for (int q = 0; q <= r; ++q) {
+        ddt = (float)((double)ddt / 2.0);
+        substeps *= 2;
+    }
+    V2 pos2 = pos;
+    for (int j = 0; j < substeps; ++j) pos2 = trace_rk3(g, u, v, ddt, pos2);
+    const float dx = FS(pos2.x, last.x), dy = FS(pos2.y, last.y);
+    const float d = sqrtf(FA(FM(dx, dx), FM(dy, dy)));
+    out = pos2;
+    return !((double)d > 0.0001 * (double)g.h) || r >= 6;
+}
+
+// updateForward, :1228-1240 (all cells): every cell, first solveODE round only, non-converged cells deferred.
 __global__ void __launch_bounds__(256) k2_forward(G2 g, const float *u, const float *v, float *fx, float *fy, float dt, WorkList wl)
 {
-    if (!SLOW) {
-        IJ(g.ni, g.nj)
-        V2 p = {fx[idx], fy[idx]}, q;
-        if (!solve_ode_quick(g, u, v, dt, p, q)) { defer(wl, idx); return; }
+    IJ(g.ni, g.nj)
+    V2 p = {fx[idx], fy[idx]}, q;
+    if (!solve_ode_quick(g, u, v, dt, p, q)) { defer(wl, idx, q); return; }
+    clamp_pos(g, q);
+    fx[idx] = q.x;
+    fy[idx] = q.y;
+}
+// one later round over the deferred cells (in place: a cell's start position is read by its own thread only)
+__global__ void __launch_bounds__(128) k2_forward_round(G2 g, const float *u, const float *v, float *fx, float *fy, float dt, int r,
+                                                        WorkList in, WorkList out, int *entered)
+{
+    const int n = *in.count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) entered[r] = n;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int idx = in.items[e];
+        const V2 p = {fx[idx], fy[idx]}, last = {in.px[e], in.py[e]};
+        V2 q;
+        if (!solve_ode_round(g, u, v, dt, r, p, last, q)) { defer(out, idx, q); continue; }
         clamp_pos(g, q);
         fx[idx] = q.x;
         fy[idx] = q.y;
-    } else {
-        const int n = *wl.count;
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-            const int idx = wl.items[e];
-            V2 p = {fx[idx], fy[idx]};
-            p = solve_ode(g, u, v, dt, p);
-            clamp_pos(g, p);
-            fx[idx] = p.x;
-            fy[idx] = p.y;
-        }
     }
 }
 
@@ -275,27 +300,31 @@ k2_backward(G2 g, const float *u, const float *v, const float *bx, const float *
     oy[idx] = sample_field(by, g.ni, g.nj, g, sx, sy);
 }
 
-// semiLagAdvect, :110-123 (same two-pass scheme as k2_forward)
-template <bool SLOW>
+// semiLagAdvect, :110-123 (same scheme as k2_forward: quick pass, then one launch per later round)
 __global__ void __launch_bounds__(256)
 k2_semilag(G2 g, const float *u, const float *v, const float *src, float *dst, int fni, int fnj, float offx, float offy,
            float dt, WorkList wl)
 {
     const float ox = FM(g.h, offx), oy = FM(g.h, offy);
-    if (!SLOW) {
-        IJ(fni, fnj)
-        V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)}, b;
-        if (!solve_ode_quick(g, u, v, -dt, pos, b)) { defer(wl, idx); return; }
+    IJ(fni, fnj)
+    V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)}, b;
+    if (!solve_ode_quick(g, u, v, -dt, pos, b)) { defer(wl, idx, b); return; }
+    dst[idx] = sample_field(src, fni, fnj, g, FS(b.x, ox), FS(b.y, oy));
+}
+__global__ void __launch_bounds__(128)
+k2_semilag_round(G2 g, const float *u, const float *v, const float *src, float *dst, int fni, int fnj, float offx, float offy,
+                 float dt, int r, WorkList in, WorkList out, int *entered)
+{
+    const float ox = FM(g.h, offx), oy = FM(g.h, offy);
+    const int n = *in.count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) entered[r] = n;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int idx = in.items[e];
+        const int i = idx % fni, j = idx / fni;
+        const V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)}, last = {in.px[e], in.py[e]};
+        V2 b;
+        if (!solve_ode_round(g, u, v, -dt, r, pos, last, b)) { defer(out, idx, b); continue; }
         dst[idx] = sample_field(src, fni, fnj, g, FS(b.x, ox), FS(b.y, oy));
-    } else {
-        const int n = *wl.count;
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-            const int idx = wl.items[e];
-            const int i = idx % fni, j = idx / fni;
-            V2 pos = {FA(FM(g.h, (float)i), ox), FA(FM(g.h, (float)j), oy)};
-            V2 b = solve_ode(g, u, v, -dt, pos);
-            dst[idx] = sample_field(src, fni, fnj, g, FS(b.x, ox), FS(b.y, oy));
-        }
     }
 }
 
@@ -528,8 +557,10 @@ struct bmq2d_solver {
     float *f[BMQ2_F_COUNT] = {};
     int fni[BMQ2_F_COUNT], fnj[BMQ2_F_COUNT];
     float *d_red = nullptr, *h_red = nullptr;
-    int *d_wl = nullptr;       // 6 work lists of wl_stride ints: [0] = counter, [1..] = deferred element indices
-    size_t wl_stride = 0;
+    // 6 work lists x 2 buffers (the rounds ping-pong) of wl_stride words: counter, then `wl_cap` cell indices, last x, last y
+    int *d_wl = nullptr;
+    size_t wl_stride = 0, wl_cap = 0;
+    int *d_round_counts = nullptr;   // [6 lists][8]: cells entering round 1..6 of the last step (diagnostic)
     cudaStream_t side[6] = {};
     cudaEvent_t ev_quick = nullptr, ev_side[6] = {};
     int pending_slow = 0;      // bit w set: slow pass w has been recorded on side[w]
@@ -603,7 +634,25 @@ int max_vel(bmq2d_solver *s, float *out)
     return BMQ_OK;
 }
 
-WorkList worklist(bmq2d_solver *s, int w) { return WorkList{s->d_wl + w * s->wl_stride, s->d_wl + w * s->wl_stride + 1}; }
+WorkList worklist(bmq2d_solver *s, int w, int buf = 0)
+{
+    int *base = s->d_wl + (size_t)(2 * w + buf) * s->wl_stride;
+    float *fl = reinterpret_cast<float *>(base);
+    return WorkList{base, base + 4, fl + 4 + s->wl_cap, fl + 4 + 2 * s->wl_cap};
+}
+// the rounds of one work list, one launch each, on its side stream; the grid covers the list of round 1 and later
+// rounds leave most CTAs idle at once (the counts stay on the device: no host round trip)
+template <typename Launch> int slow_rounds(bmq2d_solver *s, int w, Launch launch)
+{
+    for (int r = 1; r <= 6; ++r) {
+        WorkList in = worklist(s, w, (r - 1) & 1), out = worklist(s, w, r & 1);
+        BMQ_CK(cudaMemsetAsync(out.count, 0, sizeof(int), s->side[w]));
+        launch(r, in, out);
+        L2D(s);
+        BMQ_CK(cudaGetLastError());
+    }
+    return BMQ_OK;
+}
 
 // The solveODE-based kernels run in two passes (see solve_ode_quick).  The quick passes go on the
 // solver's stream; the six compacted slow passes (2 forward maps, 4 semi-Lagrangian fields) are
@@ -614,7 +663,7 @@ int forward_quick(bmq2d_solver *s, float dt, int fx, int fy, int w)
 {
     WorkList wl = worklist(s, w);
     BMQ_CK(cudaMemsetAsync(wl.count, 0, sizeof(int), s->stream));
-    k2_forward<false><<<grd(s->ni, s->nj), blk(), 0, s->stream>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, wl);
+    k2_forward<<<grd(s->ni, s->nj), blk(), 0, s->stream>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, wl);
     L2D(s);
     BMQ_CK(cudaGetLastError());
     return BMQ_OK;
@@ -622,9 +671,12 @@ int forward_quick(bmq2d_solver *s, float dt, int fx, int fy, int w)
 int forward_slow(bmq2d_solver *s, float dt, int fx, int fy, int w)
 {
     BMQ_CK(cudaStreamWaitEvent(s->side[w], s->ev_quick, 0));
-    k2_forward<true><<<148 * 4, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, worklist(s, w));
-    L2D(s);
-    BMQ_CK(cudaGetLastError());
+    {
+        int st = slow_rounds(s, w, [&](int r, WorkList in, WorkList out) {
+            k2_forward_round<<<148 * 4, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[fx], s->f[fy], dt, r, in, out, s->d_round_counts + 8 * w);
+        });
+        if (st != BMQ_OK) return st;
+    }
     BMQ_CK(cudaEventRecord(s->ev_side[w], s->side[w]));
     s->pending_slow |= 1 << w;
     return BMQ_OK;
@@ -634,7 +686,7 @@ int semilag_quick(bmq2d_solver *s, int src, int dst, float dt, int w)
     FieldGeom q = geom(s, kind_of(src));
     WorkList wl = worklist(s, w);
     BMQ_CK(cudaMemsetAsync(wl.count, 0, sizeof(int), s->stream));
-    k2_semilag<false><<<grd(q.fni, q.fnj), blk(), 0, s->stream>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst],
+    k2_semilag<<<grd(q.fni, q.fnj), blk(), 0, s->stream>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst],
                                                                q.fni, q.fnj, q.offx, q.offy, dt, wl);
     L2D(s);
     BMQ_CK(cudaGetLastError());
@@ -644,10 +696,13 @@ int semilag_slow(bmq2d_solver *s, int src, int dst, float dt, int w)
 {
     FieldGeom q = geom(s, kind_of(src));
     BMQ_CK(cudaStreamWaitEvent(s->side[w], s->ev_quick, 0));
-    k2_semilag<true><<<148 * 4, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst], q.fni, q.fnj,
-                                               q.offx, q.offy, dt, worklist(s, w));
-    L2D(s);
-    BMQ_CK(cudaGetLastError());
+    {
+        int st = slow_rounds(s, w, [&](int r, WorkList in, WorkList out) {
+            k2_semilag_round<<<148 * 4, 128, 0, s->side[w]>>>(s->g, s->f[BMQ2_F_U], s->f[BMQ2_F_V], s->f[src], s->f[dst], q.fni, q.fnj,
+                                                             q.offx, q.offy, dt, r, in, out, s->d_round_counts + 8 * w);
+        });
+        if (st != BMQ_OK) return st;
+    }
     BMQ_CK(cudaEventRecord(s->ev_side[w], s->side[w]));
     s->pending_slow |= 1 << w;
     return BMQ_OK;
@@ -799,8 +854,11 @@ int bmq2d_create(int ni, int nj, float h, float blend_coeff, bmq2d_solver **out)
         if (st == BMQ_OK) st = bmq::check_cuda(cudaMemset(s->f[id], 0, bytes), "cudaMemset", __FILE__, __LINE__);
     }
     if (st == BMQ_OK) st = bmq::check_cuda(cudaMalloc(&s->d_red, 4 * sizeof(float)), "cudaMalloc", __FILE__, __LINE__);
-    s->wl_stride = (size_t)(ni + 1) * (nj + 1) + 1;
-    if (st == BMQ_OK) st = bmq::check_cuda(cudaMalloc(&s->d_wl, sizeof(int) * 6 * s->wl_stride), "cudaMalloc", __FILE__, __LINE__);
+    s->wl_cap = (size_t)(ni + 1) * (nj + 1);
+    s->wl_stride = 4 + 3 * s->wl_cap;
+    if (st == BMQ_OK) st = bmq::check_cuda(cudaMalloc(&s->d_wl, sizeof(int) * 12 * s->wl_stride), "cudaMalloc", __FILE__, __LINE__);
+    if (st == BMQ_OK) st = bmq::check_cuda(cudaMalloc(&s->d_round_counts, sizeof(int) * 48), "cudaMalloc", __FILE__, __LINE__);
+    if (st == BMQ_OK) st = bmq::check_cuda(cudaMemset(s->d_round_counts, 0, sizeof(int) * 48), "cudaMemset", __FILE__, __LINE__);
     for (int w = 0; w < 6 && st == BMQ_OK; ++w) {
         st = bmq::check_cuda(cudaStreamCreateWithFlags(&s->side[w], cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__);
         if (st == BMQ_OK) st = bmq::check_cuda(cudaEventCreateWithFlags(&s->ev_side[w], cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
@@ -819,6 +877,7 @@ int bmq2d_destroy(bmq2d_solver *s)
     for (float *p : s->f) if (p) cudaFree(p);
     if (s->d_red) cudaFree(s->d_red);
     if (s->d_wl) cudaFree(s->d_wl);
+    if (s->d_round_counts) cudaFree(s->d_round_counts);
     for (int w = 0; w < 6; ++w) {
         if (s->side[w]) cudaStreamDestroy(s->side[w]);
         if (s->ev_side[w]) cudaEventDestroy(s->ev_side[w]);
@@ -1034,15 +1093,28 @@ int bmq2d_accumulate(bmq2d_solver *s, int frame, float dt)
     return BMQ_OK;
 }
 
-// Sizes of the six work lists of the last step (cells whose solveODE needed more than the first round): forward
-// maps (velocity, scalar), semi-Lagrangian rho, T, u, v.  Synchronises; a diagnostic, not part of the step.
+// Cells of the last step whose solveODE needed more than the first round, per work list: forward maps (velocity,
+// scalar), semi-Lagrangian rho, T, u, v.  Synchronises; a diagnostic, not part of the step.
 int bmq2d_deferred_counts(bmq2d_solver *s, int *counts6)
 {
     NEED2(s);
     if (!counts6) return bmq::set_error(BMQ_ERR_ARG, "bmq2d_deferred_counts: counts6 is null");
+    int all[48];
     BMQ_CK(cudaStreamSynchronize(s->stream));
+    BMQ_CK(cudaMemcpy(all, s->d_round_counts, sizeof all, cudaMemcpyDeviceToHost));
+    for (int w = 0; w < 6; ++w) counts6[w] = all[8 * w + 1];
+    return BMQ_OK;
+}
+// the same per round: counts36[6 * w + (r - 1)] = cells of list w that entered round r = 1..6
+int bmq2d_deferred_round_counts(bmq2d_solver *s, int *counts36)
+{
+    NEED2(s);
+    if (!counts36) return bmq::set_error(BMQ_ERR_ARG, "bmq2d_deferred_round_counts: counts36 is null");
+    int all[48];
+    BMQ_CK(cudaStreamSynchronize(s->stream));
+    BMQ_CK(cudaMemcpy(all, s->d_round_counts, sizeof all, cudaMemcpyDeviceToHost));
     for (int w = 0; w < 6; ++w)
-        BMQ_CK(cudaMemcpy(&counts6[w], s->d_wl + w * s->wl_stride, sizeof(int), cudaMemcpyDeviceToHost));
+        for (int r = 1; r <= 6; ++r) counts36[6 * w + r - 1] = all[8 * w + r];
     return BMQ_OK;
 }
 

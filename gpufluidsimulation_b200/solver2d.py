@@ -97,5 +97,11 @@ class BimocqAdvection2D:
         check(self.lib.bmq2d_deferred_counts(self._h, c), "bmq2d_deferred_counts")
         return list(c)
 
+    def deferred_round_counts(self):
+        """[list][round - 1]: cells that entered round 1..6 of solveODE in the last step (diagnostic; synchronises)."""
+        c = (C.c_int * 36)()
+        check(self.lib.bmq2d_deferred_round_counts(self._h, c), "bmq2d_deferred_round_counts")
+        return [list(c[6 * w:6 * w + 6]) for w in range(6)]
+
     def launches(self):
         return int(self.lib.bmq2d_kernel_launch_count(self._h))

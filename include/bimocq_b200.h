@@ -458,6 +458,8 @@ int bmq2d_get_stats(bmq2d_solver *s, bmq2d_stats *out);
 /* diagnostic: cells of the last step whose solveODE went past its first round, per work list (forward maps velocity /
  * scalar, semi-Lagrangian rho, T, u, v); synchronises */
 int bmq2d_deferred_counts(bmq2d_solver *s, int *counts6);
+/* the same per round: counts36[6 * list + (r - 1)] = cells that entered round r = 1..6 of solveODE */
+int bmq2d_deferred_round_counts(bmq2d_solver *s, int *counts36);
 int bmq2d_advect_host(bmq2d_solver *s, int frame, float dt, float *u, float *v, float *rho, float *T);
 int bmq2d_accumulate_host(bmq2d_solver *s, int frame, float dt, const float *u_forced, const float *v_forced,
                           float *u_final, float *v_final, const float *rho_final, const float *T_final);
