@@ -430,6 +430,18 @@ def run_gpu(args):
 
         if world == 1:
             leg("general_h", lambda: short_run(torch, dist, world, rank, dev, args, kind, n, 0.2 if L == 1.0 else 1.0, steps=min(args.steps, 6)))
+
+            def tolerance_leg():
+                # what bit-exactness costs at the reference scene's cell size: the same run with bmq_set_tolerance_mode(1)
+                # (NOT a drop-in mode: see include/bimocq_b200.h; results deviate up to 1e-3 over a run)
+                lib.bmq_set_tolerance_mode(1)
+                try:
+                    out = short_run(torch, dist, world, rank, dev, args, kind, n, 0.2, steps=min(args.steps, 6))
+                finally:
+                    lib.bmq_set_tolerance_mode(0)
+                out["note"] = "opt-in tolerance mode: every cell size on the power-of-two kernels; not bit-exact"
+                return out
+            leg("general_h_tolerance_mode", tolerance_leg)
             others = {}
             for wname in ("plume128", "rings256"):
                 if wname != args.workload:

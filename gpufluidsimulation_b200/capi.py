@@ -122,6 +122,8 @@ _PROTOS = {
     "bmq_set_gather_variant": (_I, [_I]),
     "bmq_set_fast_division": (_I, [_I]),
     "bmq_division_is_fast": (_I, [_f, _I]),
+    "bmq_set_tolerance_mode": (_I, [_I]),
+    "bmq_tolerance_mode": (_I, []),
     "bmq_ipc_export": (_I, [C.c_void_p, C.c_void_p]),
     "bmq_ipc_open": (_I, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bmq_ipc_close": (_I, [C.c_void_p]),

@@ -110,5 +110,7 @@ int bmq_set_pitch_specialisation(int on) { bmq::set_pitch_specialisation(on != 0
 int bmq_set_gather_variant(int variant) { bmq::set_gather_variant(variant); return BMQ_OK; }
 int bmq_set_fast_division(int on) { bmq::set_fast_division(on != 0); return BMQ_OK; }
 int bmq_division_is_fast(float h, int nmax) { return bmq::division_is_fast(h, nmax) ? 1 : 0; }
+int bmq_set_tolerance_mode(int on) { bmq::set_tolerance_mode(on != 0); return BMQ_OK; }
+int bmq_tolerance_mode(void) { return bmq::tolerance_mode() ? 1 : 0; }
 
 }  // extern "C"

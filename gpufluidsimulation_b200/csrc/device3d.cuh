@@ -19,6 +19,8 @@ struct Grid3 {
     float h;          // cell size
     float inv_h;      // RN(1/h) (exact when h is a power of two); NEGATED when the three-instruction division
                       // div_h() has not been verified for this h (kernels3d.cu:make_grid) -> IEEE division
+    int p2;           // host-side dispatch: take the kernels written for a power-of-two h (h is one, or the grid was
+                      // made in tolerance mode, bmq_set_tolerance_mode)
 };
 
 // p / h, correctly rounded, for the one divisor a launch ever has.  The reference divides (pos / h,

@@ -20,19 +20,23 @@ namespace bmq {
 
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<bool> g_fast_division{true};   // testing knob, see bmq_set_fast_division
+static std::atomic<bool> g_tolerance{false};      // opt-in, see bmq_set_tolerance_mode
 unsigned long long kernel_launch_count() { return g_launches.load(); }
 static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-static inline bool is_pow2_h(const Grid3 &g)
+static inline bool exact_pow2_h(int ni, int nj, int nk, float h, bool tolerance)
 {
     int e;
-    float m = frexpf(g.h, &e);
+    float m = frexpf(h, &e);
     // i*h, i*h +- h/4, +- h/2 must all be exact: (4*n+4) < 2^24
-    int nmax = g.ni > g.nj ? g.ni : g.nj;
-    nmax = nmax > g.nk ? nmax : g.nk;
-    return m == 0.5f && (long long)nmax * 4 + 8 < (1ll << 24);
+    int nmax = ni > nj ? ni : nj;
+    nmax = nmax > nk ? nmax : nk;
+    // tolerance mode: every cell size takes the kernels written for a power of two (positions in grid units by one
+    // multiplication with RN(1/h), node shortcuts, constant window fractions); exact only when h IS a power of two
+    return (m == 0.5f || tolerance) && (long long)nmax * 4 + 8 < (1ll << 24);
 }
+static inline bool is_pow2_h(const Grid3 &g) { return g.p2 != 0; }     // decided when the grid was made (make_grid)
 
 // ---- exhaustive check of div_h (device3d.cuh) for one divisor: every float p in [0, p_max]
 // (div_h takes the three-instruction path for p == 0 and p >= 2^-100, which is what gets verified)
@@ -78,7 +82,8 @@ Grid3 make_grid(int ni, int nj, int nk, float h)
 {
     Grid3 g;
     g.ni = ni; g.nj = nj; g.nk = nk; g.h = h; g.inv_h = 1.0f / h;
-    if (!is_pow2_h(g)) {
+    g.p2 = exact_pow2_h(ni, nj, nk, h, g_tolerance.load(std::memory_order_relaxed)) ? 1 : 0;
+    if (!is_pow2_h(g)) {      // (tolerance mode: p2 is set and inv_h stays the plain reciprocal)
         // positions stay inside the clamped domain plus one DMC reach; verify four times the domain
         int nmax = ni > nj ? ni : nj;
         nmax = nmax > nk ? nmax : nk;
@@ -87,6 +92,8 @@ Grid3 make_grid(int ni, int nj, int nk, float h)
     return g;
 }
 void set_fast_division(bool on) { g_fast_division.store(on); }
+void set_tolerance_mode(bool on) { g_tolerance.store(on); }
+bool tolerance_mode() { return g_tolerance.load(); }
 bool division_is_fast(float h, int nmax) { return make_grid(nmax, nmax, nmax, h).inv_h > 0.f; }
 
 // CTA shape (32, BMQ_BY, BMQ_BZ); default 32x4x1 = 128 threads.  A CTA that spans several z-planes shares the

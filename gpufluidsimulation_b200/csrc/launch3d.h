@@ -30,6 +30,8 @@ unsigned long long kernel_launch_count();
 void set_pitch_specialisation(bool on);   // testing knob, see bmq_set_pitch_specialisation
 void set_gather_variant(int v);           // testing knob, see bmq_set_gather_variant
 void set_fast_division(bool on);          // testing knob, see bmq_set_fast_division
+void set_tolerance_mode(bool on);         // opt-in, see bmq_set_tolerance_mode
+bool tolerance_mode();
 bool division_is_fast(float h, int nmax);
 // div_h (device3d.cuh) == IEEE division by h for every float in {0} U [2^-100, p_max]?  Checked on the device, cached per h.
 bool division_verified(float h, float p_max);

@@ -181,7 +181,7 @@ k_clamp_extrema_mc(const float *__restrict__ field, float *fieldTemp, bmq::Vel3 
     SRC_IJK(ni, nj, nk)
     (void)index;
     bmq::Grid3 g;
-    g.ni = ni - dimx; g.nj = nj - dimy; g.nk = nk - dimz; g.h = h; g.inv_h = -(1.0f / h);   // negative: IEEE division (device3d.cuh)
+    g.ni = ni - dimx; g.nj = nj - dimy; g.nk = nk - dimz; g.h = h; g.inv_h = -(1.0f / h); g.p2 = 0;   // negative: IEEE division (device3d.cuh)
     const float ptx = h * (float(i) + ox), pty = h * (float(j) + oy), ptz = h * (float(k) + oz);
     float3 v = get_velocity_ref_guarded(vel, g, ptx, pty, ptz);
     const float halfdt = 0.5f * dt;

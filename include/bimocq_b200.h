@@ -63,6 +63,16 @@ int bmq_set_gather_variant(int variant);
  * a grid of nmax cells per axis (1 = fast sequence in use; power-of-two h: always 1, no division at all). */
 int bmq_set_fast_division(int on);
 int bmq_division_is_fast(float h, int nmax);
+/* OPT-IN tolerance mode (default off = the bit-exact paths above).  With a cell size that is not a power of two the
+ * exact path pays for the reference's own rounding: a correctly rounded p / h per sampled coordinate, the generic
+ * 8-node centre sample, double-precision lerps in the DMC update.  In tolerance mode every cell size runs the kernels
+ * written for a power of two (one multiplication by RN(1/h), grid-unit positions, node shortcuts).  One step from
+ * identical state differs from the reference by rounding noise (<= 5e-6 relative L-inf); over a run the difference
+ * grows to ~1e-3, because the reference's DMC formula (1 - exp(-a s) in fp32) amplifies last-ulp input differences
+ * (tests/test_tolerance_mode_gpu.py).  An experiment that prices exactness, not a drop-in mode.
+ * Applies to handles and grids created afterwards; the 3D paths only. */
+int bmq_set_tolerance_mode(int on);
+int bmq_tolerance_mode(void);
 
 /* ---- peer-memory plumbing for the z-slab halo exchange over NVLink (one process per GPU).
  * bmq_ipc_export: CUDA IPC handle (64 bytes) of the allocation `dev_ptr` is the base of;
