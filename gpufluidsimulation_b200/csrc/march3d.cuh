@@ -163,6 +163,27 @@ __device__ __forceinline__ float to_cells(float p, float off_world, float off_gr
     return div_h(off_world != 0.f ? p - off_world : p, h, inv_h);
 }
 
+// The same for a pair of positions.  General h: the verified division sequence as three PACKED instructions for
+// both lanes behind ONE range test (the scalar form tests each lane: 2 x (2 compares + 3) instructions); a lane that
+// is exactly 0 -- a position clamped to the lower wall -- or tiny sends the pair down the scalar path.
+template <bool GRID>
+__device__ __forceinline__ float2 to_cells2(float2 p, float off_world, float off_grid, float h, float inv_h)
+{
+    if (GRID) return make_float2(to_cells<true>(p.x, off_world, off_grid, h, inv_h), to_cells<true>(p.y, off_world, off_grid, h, inv_h));
+#if defined(BMQ_NO_PACKED_FP32) || defined(BMQ_DIV_SCALAR)
+    return make_float2(to_cells<false>(p.x, off_world, off_grid, h, inv_h), to_cells<false>(p.y, off_world, off_grid, h, inv_h));
+#else
+    if (off_world != 0.f) p = make_float2(p.x - off_world, p.y - off_world);
+    if (inv_h > 0.f && fminf(fabsf(p.x), fabsf(p.y)) >= BMQ_DIV_TINY) {
+        const float2 y = make_float2(inv_h, inv_h), mh = make_float2(-h, -h);
+        const float2 q0 = __fmul2_rn(p, y);
+        const float2 r = __ffma2_rn(mh, q0, p);
+        return __ffma2_rn(r, y, q0);
+    }
+    return make_float2(div_h(p.x, h, inv_h), div_h(p.y, h, inv_h));
+#endif
+}
+
 struct Split2 {
     float2 f, omf;
     int i0, i1;
@@ -394,12 +415,9 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 float2 qx, qy, qz;
-                qx.x = to_cells<P2>(clampf(px[ii].x, lo, hix), ox, DX * 0.5f, h, g.inv_h);
-                qx.y = to_cells<P2>(clampf(px[ii].y, lo, hix), ox, DX * 0.5f, h, g.inv_h);
-                qy.x = to_cells<P2>(clampf(py[ii].x, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
-                qy.y = to_cells<P2>(clampf(py[ii].y, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
-                qz.x = to_cells<P2>(clampf(pz[ii].x, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
-                qz.y = to_cells<P2>(clampf(pz[ii].y, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
+                qx = to_cells2<P2>(make_float2(clampf(px[ii].x, lo, hix), clampf(px[ii].y, lo, hix)), ox, DX * 0.5f, h, g.inv_h);
+                qy = to_cells2<P2>(make_float2(clampf(py[ii].x, lo, hiy), clampf(py[ii].y, lo, hiy)), oy, DY * 0.5f, h, g.inv_h);
+                qz = to_cells2<P2>(make_float2(clampf(pz[ii].x, lo, hiz), clampf(pz[ii].y, lo, hiz)), oz, DZ * 0.5f, h, g.inv_h);
                 const Split2 spx = split2(qx), spy = split2(qy), spz = split2(qz);
                 float s0[NS];
                 gather_pair<NS>(a.src, fi, fplane, spx, spy, spz, s0, late[ii], hack_zero);
