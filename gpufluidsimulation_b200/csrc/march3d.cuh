@@ -41,6 +41,9 @@ enum { GM_ADVECT = 0, GM_ERROR = 1, GM_CUMULATE = 2, GM_APPLY = 3 };
 #ifndef BMQ_MARCH_PF_STREAM
 #define BMQ_MARCH_PF_STREAM 1   // prefetch the next cell's streamed (non-gathered) operands (error / accumulate kernels)
 #endif
+#ifndef BMQ_MARCH_EARLY_CENTRE
+#define BMQ_MARCH_EARLY_CENTRE 0
+#endif
 #ifndef BMQ_MARCH_PF_ROWS
 #define BMQ_MARCH_PF_ROWS 2     // field rows prefetched around the centre sample's base node (2: j, j+1; 3: also j-1)
 #endif
@@ -380,6 +383,17 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
         }
 #endif
         if (gk) {
+            // BMQ_MARCH_EARLY_CENTRE: with a power-of-two h and three window planes the centre sample's position is the
+            // centre-line value of the CARRIED middle plane, so its gathers can be issued before this cell's new map
+            // plane is even requested and travel while it loads
+            constexpr bool EARLY = BMQ_MARCH_EARLY_CENTRE && P2 && NZ == 3;
+            int zi = 0, oc = 0;
+            if (EARLY) {
+                const float qcx = to_cells<P2>(clampf(Px[1].c * ps, lo, hix), ox, DX * 0.5f, h, g.inv_h);
+                const float qcy = to_cells<P2>(clampf(Py[1].c * ps, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
+                const float qcz = to_cells<P2>(clampf(Pz[1].c * ps, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
+                oc = gather_one<NS>(a.src, fi, fplane, qcx, qcy, qcz, val, zi);
+            }
             const int onew = mbase + sz * (NZ == 3 ? k + 1 : k);
             Px[SN] = plane_xy<P2, STAG>(m.x + onew, sy, ax, ay);
             Py[SN] = plane_xy<P2, STAG>(m.y + onew, sy, ax, ay);
@@ -428,11 +442,12 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
             for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
                 for (int f = 0; f < NS; ++f) sum[f] = fmaf(wgt[f], late[ii][f], sum[f]);
-            const float qcx = to_cells<P2>(clampf(ccx, lo, hix), ox, DX * 0.5f, h, g.inv_h);
-            const float qcy = to_cells<P2>(clampf(ccy, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
-            const float qcz = to_cells<P2>(clampf(ccz, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
-            int zi;
-            const int oc = gather_one<NS>(a.src, fi, fplane, qcx, qcy, qcz, val, zi);
+            if (!EARLY) {
+                const float qcx = to_cells<P2>(clampf(ccx, lo, hix), ox, DX * 0.5f, h, g.inv_h);
+                const float qcy = to_cells<P2>(clampf(ccy, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
+                const float qcz = to_cells<P2>(clampf(ccz, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
+                oc = gather_one<NS>(a.src, fi, fplane, qcx, qcy, qcz, val, zi);
+            }
             if (BMQ_MARCH_PREFETCH && k + 1 < kb && zi + BMQ_MARCH_PF_DIST < fk) {
                 // the field plane the next cell's samples will newly touch: two planes above the centre sample's cell
 #pragma unroll
