@@ -214,9 +214,11 @@ k_dmc(Grid3 g_, int kbeg, int kend_, int kchunk, Vel3 vel, MapSetRO<NMAP> in, Ma
             tz = v0.z > 0.f ? pz - h : pz + h;
             v1 = get_velocity_ref(vel, g, tx, ty, tz);
         }
-        const float ax = (v0.x - v1.x) / (px - tx);
-        const float ay = (v0.y - v1.y) / (py - ty);
-        const float az = (v0.z - v1.z) / (pz - tz);
+        // power-of-two h: px - tx is exactly +-h (both are exact multiples of h), and dividing by +-h is the exact
+        // multiplication by +-1/h -- the same bits as the reference's division without three IEEE divisions
+        const float ax = P2 ? (v0.x - v1.x) * (v0.x > 0.f ? g.inv_h : -g.inv_h) : (v0.x - v1.x) / (px - tx);
+        const float ay = P2 ? (v0.y - v1.y) * (v0.y > 0.f ? g.inv_h : -g.inv_h) : (v0.y - v1.y) / (py - ty);
+        const float az = P2 ? (v0.z - v1.z) * (v0.z > 0.f ? g.inv_h : -g.inv_h) : (v0.z - v1.z) / (pz - tz);
         const float nx = dmc_axis(px, v0.x, ax, substep);
         const float ny = dmc_axis(py, v0.y, ay, substep);
         const float nz = dmc_axis(pz, v0.z, az, substep);
