@@ -134,6 +134,12 @@ static inline dim3 grid3_columns(int fi, int fj, KRange r, int kc)
 // Column form of the same index space: a thread owns cells (i, j, kc0..kc1) and walks them in z, so that the planes
 // k-1, k, k+1 its gathers touch are still in L1 when the next cell needs them (a CTA per plane re-fetched them from
 // L2 for every plane).  The map-update and distortion kernels use it; kchunk = 1 is the old one-cell-per-thread form.
+// launch bounds of the three column kernels (CTAs of 128 threads): BMQ_MAPK_MINBLOCKS caps the registers per thread
+#ifndef BMQ_MAPK_MINBLOCKS
+#define BMQ_MAPK_BOUNDS __launch_bounds__(256)
+#else
+#define BMQ_MAPK_BOUNDS __launch_bounds__(128, BMQ_MAPK_MINBLOCKS)
+#endif
 #define BMQ_COLUMN(fi, fj)                                       \
     const int i = blockIdx.x * 32 + threadIdx.x;                 \
     const int j = blockIdx.y * BMQ_BY + threadIdx.y;             \
@@ -147,7 +153,7 @@ static inline dim3 grid3_columns(int fi, int fj, KRange r, int kc)
 // forward_kernel, GPU_kernel.cu:127-144: psi <- trace(psi, +dt) in place, NMAP mappers at once
 // (each mapper's particle is independent; tracing two per thread doubles the loads in flight).
 template <bool P2, int NMAP, int FIX = 0>
-__global__ void __launch_bounds__(256)
+__global__ void BMQ_MAPK_BOUNDS
 k_forward(Grid3 g_, int kbeg, int kend_, int kchunk, Vel3 vel, MapSetRW<NMAP> maps, float cfldt, float dt)
 {
     const Grid3 g = fix_grid<FIX>(g_);
@@ -182,7 +188,7 @@ __device__ __forceinline__ float dmc_axis(float p, float v, float a, float s)
 }
 
 template <bool P2, int NMAP, int FIX = 0>
-__global__ void __launch_bounds__(256)
+__global__ void BMQ_MAPK_BOUNDS
 k_dmc(Grid3 g_, int kbeg, int kend_, int kchunk, Vel3 vel, MapSetRO<NMAP> in, MapSetRW<NMAP> out, float substep)
 {
     const Grid3 g = fix_grid<FIX>(g_);
@@ -570,7 +576,14 @@ k_double_advect(Grid3 g, int kbeg, int kend_, Stag st, bool is_point, FieldSetRW
 // reference does on the host (Mapping.cpp:100-117) fused in: warp shuffle -> block -> one
 // atomicMax per block.  Also reduces max |map_z - z| (in world units) per mapper for halo sizing.
 template <bool P2, int NMAP, int FIX = 0>
-__global__ void __launch_bounds__(256)
+// power-of-two h: 80 registers (six CTAs of 128 threads per SM) let the four independent map samples of a cell keep
+// their 96 loads in flight: 4.35 -> 2.78 ms at 512^3; with a general h the same budget is slower (4.8 -> 5.3 ms), and
+// so are the DMC and forward kernels with any larger budget (profiles/r2_march_variants.md)
+#ifndef BMQ_MAPK_MINBLOCKS
+__global__ void __launch_bounds__(P2 ? 128 : 256, P2 ? 6 : 1)
+#else
+__global__ void BMQ_MAPK_BOUNDS
+#endif
 k_estimate(Grid3 g_, int kbeg, int kend_, int kchunk, MapSetRO<NMAP> bwd, MapSetRO<NMAP> fwd, DistOut<NMAP> outp,
            const signed char *__restrict__ boundary)
 {
