@@ -724,7 +724,10 @@ bool march_is_pow2_h(const Grid3 &g) { return is_pow2_h(g); }
 // Same arithmetic, bit-identical results; the knob lets tests and benchmarks compare the two.
 static std::atomic<int> g_gather_variant{1};
 void set_gather_variant(int v) { g_gather_variant.store(v); }
-static inline bool use_march() { return g_gather_variant.load(std::memory_order_relaxed) == 1; }
+// 0: windowed kernels (round 1); 1: z-marching kernels, clamp fused into the apply kernel; 2: z-marching kernels, the
+// clamp as its own shared-memory tiled kernel (clamp27.cu)
+static inline bool use_march() { return g_gather_variant.load(std::memory_order_relaxed) >= 1; }
+static inline bool split_clamp() { return g_gather_variant.load(std::memory_order_relaxed) == 2; }
 #define DISPATCH_P2_FIX(g, KERNEL, NM, ...)                                                     \
     do {                                                                                        \
         switch (fix_of(g) * 2 + (is_pow2_h(g) ? 1 : 0)) {                                       \
@@ -958,6 +961,10 @@ cudaError_t launch_apply_clamp(cudaStream_t s, const Grid3 &g, KRange r, Stag st
     dim3 gr = grid3(g.ni + st.dx, g.nj + st.dy, r), bl = block3();
     if (!is_point && (nf == 1 || stag_id(st) == 0) && use_march()) {
         count_launch();
+        if (split_clamp()) {
+            count_launch();
+            return launch_apply_march_split(s, g, r, st, nf, out, fadv, e0, chi);
+        }
         return launch_apply_march(s, g, r, st, nf, out, fadv, e0, chi);
     }
     if (!is_point && (nf == 1 || stag_id(st) == 0)) {

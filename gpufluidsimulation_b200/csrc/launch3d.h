@@ -46,6 +46,9 @@ cudaError_t launch_cumulate_march(cudaStream_t s, const Grid3 &g, KRange r, Stag
                                   const float *const map[3]);
 cudaError_t launch_apply_march(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, float *const *out,
                                const float *const *fadv, const float *const *e0, const float *const chi[3]);
+cudaError_t launch_apply_march_split(cudaStream_t s, const Grid3 &g, KRange r, Stag st, int nf, float *const *out,
+                               const float *const *fadv, const float *const *e0, const float *const chi[3]);
+cudaError_t launch_clamp27(cudaStream_t s, int fi, int fj, int fk, KRange r, int nf, const float *const *before, float *const *f);
 
 cudaError_t launch_forward(cudaStream_t s, const Grid3 &g, KRange r, const float *u, const float *v,
                            const float *w, int nmap, float *const maps[][3], float cfldt, float dt);

@@ -27,7 +27,9 @@
 
 namespace bmq {
 
-enum { GM_ADVECT = 0, GM_ERROR = 1, GM_CUMULATE = 2, GM_APPLY = 3 };
+// GM_APPLY_NC: the apply kernel without its extrema clamp (the clamp then runs as a separate shared-memory tiled
+// stencil kernel, clamp27.cu: bmq_set_gather_variant(2))
+enum { GM_ADVECT = 0, GM_ERROR = 1, GM_CUMULATE = 2, GM_APPLY = 3, GM_APPLY_NC = 4 };
 
 #ifndef BMQ_MARCH_BY
 #define BMQ_MARCH_BY 4          // CTA = 32 x BMQ_MARCH_BY columns
@@ -330,7 +332,8 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
     const float hiz = (MODE == GM_ADVECT ? h * (float)g.nk - h : h * (float)g.nk) * ps;
     const int col = i + fi * j, fplane = fi * fj;
 
-    if (MODE != GM_APPLY) {
+    constexpr bool APPLYISH = MODE == GM_APPLY || MODE == GM_APPLY_NC;
+    if (!APPLYISH) {
         if (!gij || ka >= kb) return;
     } else if (!(i > 0 && i < fi - 1 && j > 0 && j < fj - 1)) {
         // rim columns of the apply kernel: f = f_adv (the reference leaves f_adv untouched there)
@@ -351,7 +354,7 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
     PlaneXY Px[3], Py[3], Pz[3];  // map planes of the current window (z nodes 0..NZ-1)
     Plane9 M[NF][3];              // apply: ring of 3x3 extrema of f_adv planes k-1, k, k+1
     const bool gathers = gij && ka < kb;
-    const int kfirst = MODE == GM_APPLY ? kc0 : ka, klast = MODE == GM_APPLY ? kc1 : kb;
+    const int kfirst = APPLYISH ? kc0 : ka, klast = APPLYISH ? kc1 : kb;
 
     // One cell: z node n of its window is Px/Py/Pz[n]; the newest plane is loaded here, the others are carried.
     // (Unrolling the k loop by the ring period instead of moving the planes down was measured: 3-6x the code,
@@ -360,7 +363,7 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
         constexpr int S0 = 0, S1 = 1, S2 = NZ == 3 ? 2 : 0;
         constexpr int SN = NZ - 1;                                           // slot the new plane goes to
         const int idx = col + fplane * k;
-        const bool gk = MODE != GM_APPLY || (gathers && k >= ka && k < kb);
+        const bool gk = !APPLYISH || (gathers && k >= ka && k < kb);
         float sum[NS], val[NS];
 #pragma unroll
         for (int f = 0; f < NS; ++f) sum[f] = val[f] = 0.f;
@@ -388,12 +391,14 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
             // plane is even requested and travel while it loads
             constexpr bool EARLY = BMQ_MARCH_EARLY_CENTRE && P2 && NZ == 3;
             int zi = 0, oc = 0;
+#if BMQ_MARCH_EARLY_CENTRE
             if (EARLY) {
                 const float qcx = to_cells<P2>(clampf(Px[1].c * ps, lo, hix), ox, DX * 0.5f, h, g.inv_h);
                 const float qcy = to_cells<P2>(clampf(Py[1].c * ps, lo, hiy), oy, DY * 0.5f, h, g.inv_h);
                 const float qcz = to_cells<P2>(clampf(Pz[1].c * ps, lo, hiz), oz, DZ * 0.5f, h, g.inv_h);
                 oc = gather_one<NS>(a.src, fi, fplane, qcx, qcy, qcz, val, zi);
             }
+#endif
             const int onew = mbase + sz * (NZ == 3 ? k + 1 : k);
             Px[SN] = plane_xy<P2, STAG>(m.x + onew, sy, ax, ay);
             Py[SN] = plane_xy<P2, STAG>(m.y + onew, sy, ax, ay);
@@ -423,7 +428,7 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
             for (int c = 0; c < NCH; ++c)
 #pragma unroll
                 for (int f = 0; f < NF; ++f)
-                    wgt[c * NF + f] = MODE == GM_CUMULATE ? 0.125f * a.coeff[c] : MODE == GM_APPLY ? 0.125f * -0.5f : 0.125f;
+                    wgt[c * NF + f] = MODE == GM_CUMULATE ? 0.125f * a.coeff[c] : APPLYISH ? 0.125f * -0.5f : 0.125f;
             // corner samples ii and ii + 4 as one packed pair; the x-minus halves wait for their turn in the sum
             float late[4][NS];
 #pragma unroll
@@ -475,6 +480,13 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
                 }
                 a.out[f][idx] = t;
             }
+        } else if (MODE == GM_APPLY_NC) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float r = __ldg(a.aux[f] + idx);
+                if (gk) r += fmaf(0.5f, sum[f], 0.5f * (-0.5f * val[f]));
+                a.out[f][idx] = r;
+            }
         } else {
             constexpr int Q0 = 0, Q1 = 1, Q2 = 2;     // extrema of planes k-1, k, k+1
             const bool clamps = k > 0 && k < fk - 1;
@@ -513,7 +525,7 @@ k_march(Grid3 g_, int kbeg, int kend, int kchunk, MarchArgs<NF, NF * NCH> a, Map
 #pragma unroll 1
     for (int k = kfirst; k < klast; ++k) {
         body(k);
-        if (MODE != GM_APPLY || (gathers && k >= ka && k < kb)) {
+        if (!APPLYISH || (gathers && k >= ka && k < kb)) {
             Px[0] = Px[1]; Py[0] = Py[1]; Pz[0] = Pz[1];
             if (NZ == 3) { Px[1] = Px[2]; Py[1] = Py[2]; Pz[1] = Pz[2]; }
         }

@@ -52,7 +52,8 @@ unsigned long long bmq_kernel_launch_count(void);
  * switches them off so that tests can compare the two paths bit for bit.  Default: on. */
 int bmq_set_pitch_specialisation(int on);
 /* Testing knob.  The advect / error / apply / accumulate gathers run as z-marching column kernels
- * (variant 1, default: a thread keeps the x-y-interpolated map planes of its column in registers) or as
+ * (variant 1: a thread keeps the x-y-interpolated map planes of its column in registers, the extrema clamp fused
+ * into the apply kernel), the same with the clamp as its own shared-memory tiled stencil kernel (variant 2), or as
  * one windowed cell per thread (variant 0).  Same arithmetic, bit-identical results. */
 int bmq_set_gather_variant(int variant);
 /* Division by the cell size.  The reference computes pos / h (GPU_kernel.cu:46-51); when h is not a power

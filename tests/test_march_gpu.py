@@ -41,17 +41,20 @@ def _run(variant, dims, L, blend, frames, dt):
 def test_march_is_bit_identical_to_windowed(cuda, dims, L, blend):
     frames, dt = 4, 0.02
     a = _run(0, dims, L, blend, frames, dt)
-    b = _run(1, dims, L, blend, frames, dt)
-    for frame in range(frames):
-        for name in CHECK:
-            assert np.array_equal(a[frame][name], b[frame][name]), (frame, name, float(np.abs(a[frame][name] - b[frame][name]).max()))
+    # 1: clamp fused into the apply kernel; 2: the clamp as its own shared-memory tiled kernel (clamp27.cu)
+    for variant in (1, 2):
+        b = _run(variant, dims, L, blend, frames, dt)
+        for frame in range(frames):
+            for name in CHECK:
+                assert np.array_equal(a[frame][name], b[frame][name]), (variant, frame, name, float(np.abs(a[frame][name] - b[frame][name]).max()))
     # the scene really moves: the comparison is not one of untouched buffers
     assert np.abs(a[-1]["U"] - a[0]["U"]).max() > 0
 
 
-def test_march_on_slab_ranges(cuda):
-    """Columns cut by slab boundaries (owned ranges of 5-7 planes): slab ranks on the marching kernels vs a
-    single windowed solver."""
+@pytest.mark.parametrize("variant", [1, 2])
+def test_march_on_slab_ranges(cuda, variant):
+    """Columns cut by slab boundaries (owned ranges of 5-7 planes): slab ranks on the marching kernels (clamp fused /
+    clamp as its own tiled kernel) vs a single windowed solver."""
     from gpufluidsimulation_b200.solver3d import BimocqAdvection3D
     lib = load_library()
     ni, nj, nk, dt, world, halo = 32, 28, 26, 0.02, 4, 10
@@ -72,7 +75,7 @@ def test_march_on_slab_ranges(cuda):
         for frame in range(3):
             lib.bmq_set_gather_variant(0)
             single.advect(frame, dt); single.apply_buoyancy(0.2, dt); single.accumulate(frame, dt)
-            lib.bmq_set_gather_variant(1)
+            lib.bmq_set_gather_variant(variant)
             st.advect(frame, dt)
             for r in ranks:
                 r.solver.apply_buoyancy(0.2, dt)
