@@ -180,3 +180,71 @@ def test_gloo_slab_ranks_match_single_domain_oracle(oracle, world, blend, halo):
         assert halo < 5 or all(w <= halo for _, _, w in log)
         for name, (kb, arr) in owned.items():
             assert np.array_equal(arr, want[name][kb:kb + arr.shape[0]]), (rank, name)
+
+
+def _single_domain_reference(oracle, ni, nj, nk, frames, blend, cfl, dt=0.02):
+    h = 1.0 / ni
+    full = list(scenes.smoke_plume(ni, nj, nk, 1.0))
+    full[:3] = scenes.scale_to_cfl(*full[:3], h, dt, cfl)
+    s = oracle.Solver(ni, nj, nk, h, blend)
+    s.set_initial(*full)
+    log = []
+    for frame in range(frames):
+        s.advect(frame, dt)
+        adv = [a.copy() for a in s.cur]
+        dv = np.zeros_like(adv[1])
+        dv[:, 1:-1, :] = np.float32(0.5 * dt * 0.2) * (adv[4][:, 1:, :] + adv[4][:, :-1, :])
+        final = [adv[0], adv[1] + dv, adv[2], adv[3], adv[4]]
+        z = lambda a: oracle.padded(a.shape)
+        for c in range(5):
+            s.cur[c][...] = final[c]
+        s.accumulate_changes(frame, dt, [z(adv[0]), oracle.padded_copy(dv), z(adv[2])], [z(adv[0]), z(adv[1]), z(adv[2])],
+                             [z(adv[3]), z(adv[4])])
+        log.append((s.stats["vel_reinit"], s.stats["scalar_reinit"]))
+    want = dict(zip(zslab.CUR, s.cur)); want.update(zip(zslab.INIT, s.init))
+    want.update(zip(zslab.MAPS_BWD, s.vel.bwd + s.sca.bwd)); want.update(zip(zslab.MAPS_FWD, s.vel.fwd + s.sca.fwd))
+    return want, log
+
+
+# cfl 1.5: two DMC sub-steps, widths >= 5, so the first chi exchange is skipped from the second frame on; cfl 0.7: one
+# sub-step, widths of 4 < NARROW, nothing may be skipped; halo 3: the allocation has to grow in the first frame
+@pytest.mark.parametrize("world,blend,halo,cfl", [(3, 1.0, 10, 1.5), (4, 0.5, 10, 1.5), (3, 1.0, 10, 0.7), (2, 0.5, 3, 1.5)])
+def test_c_driver_schedule_on_logical_oracle_ranks(oracle, world, blend, halo, cfl):
+    """The exchange schedule of bmq3d_mg_* (velocity halo posted with a guessed width, chi exchange skipped while the
+    halo is still valid, change fields in two exchanges) restated in tests/zslab_fast_schedule.py, on oracle-backed
+    logical ranks: owned planes, maps and re-initialisation frames must match the single-domain oracle bit for bit."""
+    sys.path.insert(0, HERE)
+    from oracle_slab_rank import OracleSlabRank
+    from zslab_fast_schedule import FastScheduleStepper
+    ni, nj, nk, frames, dt = 16, 20, 36, 5, 0.02
+    h = 1.0 / ni
+    full = list(scenes.smoke_plume(ni, nj, nk, 1.0))
+    full[:3] = scenes.scale_to_cfl(*full[:3], h, dt, cfl)
+    full = [np.ascontiguousarray(a, dtype=np.float32) for a in full]
+    ranks = [OracleSlabRank(ni, nj, nk, h, blend, r, world, halo) for r in range(world)]
+    for r in ranks:
+        r.set_initial(full)
+    st = FastScheduleStepper(ranks, zslab.LocalComm(world), blend)
+    log = []
+    for frame in range(frames):
+        st.advect(frame, dt)
+        for r in ranks:
+            T, V, dV = r.f["T"], r.f["V"], r.f["DV_EXT"]
+            dV[:, 1:-1, :] = np.float32(0.5 * dt * 0.2) * (T[:, 1:, :] + T[:, :-1, :])
+            V += dV
+        st.accumulate(frame, dt)
+        log.append((st.stats["vel_reinit"], st.stats["scalar_reinit"]))
+    want, ref_log = _single_domain_reference(oracle, ni, nj, nk, frames, blend, cfl, dt)
+    assert log == ref_log
+    for r in ranks:
+        for name in zslab.CUR + zslab.INIT + zslab.MAPS_BWD + zslab.MAPS_FWD:
+            dz = 1 if name in zslab.W_TYPE else 0
+            kb, ke = r.own(dz)
+            p0 = r.p0[name]
+            assert np.array_equal(r.f[name][kb - p0:ke - p0], want[name][kb:ke]), (r.rank, name)
+    if cfl > 1.0 and halo >= 5:
+        assert st.skipped_chi >= 2, st.skipped_chi       # the shortcut was actually taken (whenever the last widths were >= 5)
+    if cfl < 1.0:
+        assert st.skipped_chi == 0 or any(a or b for a, b in log), st.skipped_chi   # widths of 4: only a re-initialisation validates the halo
+    if halo < 5:
+        assert st.grow_count >= 1
