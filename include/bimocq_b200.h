@@ -69,8 +69,8 @@ int bmq_division_is_fast(float h, int nmax);
  * 8-node centre sample, double-precision lerps in the DMC update.  In tolerance mode every cell size runs the kernels
  * written for a power of two (one multiplication by RN(1/h), grid-unit positions, node shortcuts).  One step from
  * identical state differs from the reference by rounding noise (<= 5e-6 relative L-inf); over a run the difference
- * grows to ~1e-3, because the reference's DMC formula (1 - exp(-a s) in fp32) amplifies last-ulp input differences
- * (tests/test_tolerance_mode_gpu.py).  An experiment that prices exactness, not a drop-in mode.
+ * grows to ~1e-3, because the reference's DMC formula (1 - exp(-a s) in fp32) amplifies relative differences of its
+ * velocity input several hundred times (tests/test_tolerance_mode_gpu.py, tests/test_oracle_cpu.py).  An experiment that prices exactness, not a drop-in mode.
  * Applies to handles and grids created afterwards; the 3D paths only. */
 int bmq_set_tolerance_mode(int on);
 int bmq_tolerance_mode(void);

@@ -133,3 +133,36 @@ def test_scheduler_distortion_trigger(oracle):
         last_v = f if st["vel_reinit"] else last_v
         last_s = f if st["scalar_reinit"] else last_s
     assert sum(st["vel_reinit"] for st in log) >= 2
+
+
+def test_dmc_formula_amplifies_last_ulp_velocity_differences(oracle):
+    """Why only bit-identical upstream arithmetic reproduces the reference's maps ("What exactness
+    costs"): the DMC update evaluates 1 - exp(-a s) in fp32 (GPU_kernel.cu:194-196), which cancels for the usual
+    a s << 1.  Here the oracle's DMC kernel runs twice on the benchmark scene (h = 0.2 / 64, one CFL sub-step from
+    identity maps), the second time with every velocity value moved by +-1 ulp: the back-traced points move by tens
+    of micro-cells -- hundreds of times what a 1.2e-7 relative change of a <= 1 cell displacement would explain."""
+    from gpufluidsimulation_b200 import scenes
+    ni, nj, nk, L, dt = 48, 40, 56, 0.2, 0.02
+    h = float(np.float32(L / ni))
+    u, v, w, _, _ = scenes.smoke_plume(ni, nj, nk, L)
+    u, v, w = scenes.scale_to_cfl(u, v, w, h, dt, 1.5)
+    sub = float(np.float32(h) / np.float32(max(float(np.abs(a).max()) for a in (u, v, w))))
+
+    def run(vel):
+        U, V, W = (oracle.padded_copy(a) for a in vel)
+        ident = oracle.identity_maps(ni, nj, nk, h)
+        out = [oracle.padded(a.shape) for a in ident]
+        oracle.gpu_solve_backwardDMC(U, V, W, *ident, *out, h, ni, nj, nk, sub)
+        return out
+
+    rng = np.random.default_rng(7)
+
+    def one_ulp(a):
+        up = rng.integers(0, 2, a.shape).astype(bool)
+        return np.where(up, np.nextafter(a, np.float32(np.inf)), np.nextafter(a, np.float32(-np.inf))).astype(np.float32)
+
+    base, moved = run((u, v, w)), run((one_ulp(u), one_ulp(v), one_ulp(w)))
+    worst_cells = max(float(np.abs(a - b).max()) for a, b in zip(base, moved)) / h
+    plain = 1.2e-7 * 1.0          # a displacement of at most one cell, changed by one ulp of the velocity
+    assert worst_cells > 50 * plain, worst_cells          # amplified (measured: ~2e-5 .. 5e-5 cells)
+    assert worst_cells < 1e-3, worst_cells                # ... but not broken
